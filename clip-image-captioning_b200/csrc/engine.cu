@@ -1,0 +1,1003 @@
+// libclipcap_b200: context, weight ingestion, the three forward stages (ViT -> prefix mapper -> LM) and the
+// on-device generation loops behind the C ABI of include/clipcap_b200.h.
+//
+// Everything here is host orchestration of the kernels in gemm.cu / rowwise.cu / attention.cu / sampler.cu:
+// no allocation and no host synchronisation after ccb_create (ccb_generate replays a captured CUDA graph per
+// decode step on an internal stream that is fenced against the caller's stream with events).
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "engine.h"
+
+using namespace ccb;
+
+namespace {
+
+thread_local char g_create_err[512] = "";
+
+int fail(ccb_ctx* c, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (c)
+    c->err = buf;
+  else
+    snprintf(g_create_err, sizeof(g_create_err), "%s", buf);
+  return -1;
+}
+
+// run one internal launcher (returns 0 / cudaError / -1 with gemm_last_error) and account for it
+#define RUN(call)                                                                                      \
+  do {                                                                                                 \
+    const int r__ = (call);                                                                            \
+    if (r__ != 0) {                                                                                    \
+      return fail(c, "%s failed: %s", #call,                                                           \
+                  r__ == -1 ? gemm_last_error() : cudaGetErrorString(static_cast<cudaError_t>(r__)));  \
+    }                                                                                                  \
+    if (c->capturing) c->capture_launches++; else c->launches++;                                       \
+  } while (0)
+
+#define CUDA_OK(call)                                                                   \
+  do {                                                                                  \
+    const cudaError_t e__ = (call);                                                     \
+    if (e__ != cudaSuccess) return fail(c, "%s: %s", #call, cudaGetErrorString(e__));   \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------ small kernels
+__global__ void init_state_kernel(int* block_table, int* block_table_prefill, int max_pages, int rows, int N, int beam,
+                                  int S0, int T, int page_tokens, int pages_per_row, int* ctx_len, int* step,
+                                  int* lengths, int* stops, uint8_t* finished, float* scores, float* seq_lengths,
+                                  uint8_t* has_stopped) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nth = gridDim.x * blockDim.x;
+  if (beam <= 1) {
+    // row r owns pages [r * pages_per_row, (r+1) * pages_per_row)
+    for (int i = tid; i < rows * pages_per_row; i += nth) {
+      const int r = i / pages_per_row, j = i % pages_per_row;
+      block_table[static_cast<long long>(r) * max_pages + j] = i;
+      block_table_prefill[static_cast<long long>(r) * max_pages + j] = i;
+    }
+  } else {
+    // token-granular pages (page_tokens == 1).  Image n owns pages [n * ppi, (n+1) * ppi), ppi = S0 + beam * T:
+    // the first S0 hold the prefix shared by all beams; row k's token written at step j goes to
+    // S0 + j * beam + k.  beam_step permutes the entries [0, ctx) of a row, never the fresh ones.
+    const int ppi = S0 + beam * T;
+    for (int i = tid; i < rows * (S0 + T); i += nth) {
+      const int r = i / (S0 + T), j = i % (S0 + T);
+      const int n = r / beam, k = r % beam;
+      const int page = (j < S0) ? n * ppi + j : n * ppi + S0 + (j - S0) * beam + k;
+      block_table[static_cast<long long>(r) * max_pages + j] = page;
+      if (k == 0 && j < S0) block_table_prefill[static_cast<long long>(n) * max_pages + j] = page;
+    }
+  }
+  for (int r = tid; r < rows; r += nth) {
+    ctx_len[r] = S0;
+    lengths[r] = 0;
+    stops[r] = 0;
+    finished[r] = 0;
+    scores[r] = 0.f;
+    seq_lengths[r] = 1.f;
+    has_stopped[r] = 0;
+  }
+  if (tid == 0) *step = 0;
+}
+
+__global__ void finalize_beam_kernel(const float* scores, const float* seq_lengths, int rows, int* lengths_out,
+                                     float* scores_out) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const float len = seq_lengths[r];
+  if (lengths_out) lengths_out[r] = static_cast<int>(len);
+  if (scores_out) scores_out[r] = scores[r] / len;  // inference.py:138
+}
+
+// out[n, row_off, :] = wte[token, :]  (BOS embedding appended after the prefix, evaluate_model.py:124-133)
+__global__ void token_rows_kernel(const bf16* __restrict__ wte, int token, float* __restrict__ out,
+                                  long long image_stride, long long row_off, int d) {
+  const bf16* src = wte + static_cast<long long>(token) * d;
+  float* dst = out + blockIdx.x * image_stride + row_off * d;
+  for (int cidx = threadIdx.x; cidx < d; cidx += blockDim.x) dst[cidx] = __bfloat162float(src[cidx]);
+}
+
+// dst[(r / gi) * dgo + r % gi, :] = src[(r / gi) * sgo + soff + r % gi, :]
+__global__ void regroup_rows_kernel(const float* __restrict__ src, int gi, int sgo, int soff, float* __restrict__ dst,
+                                    int dgo, int d) {
+  const int r = blockIdx.x;
+  const float4* s4 = reinterpret_cast<const float4*>(src + (static_cast<long long>(r / gi) * sgo + soff + r % gi) * d);
+  float4* d4 = reinterpret_cast<float4*>(dst + (static_cast<long long>(r / gi) * dgo + r % gi) * d);
+  for (int cidx = threadIdx.x; cidx < d / 4; cidx += blockDim.x) d4[cidx] = s4[cidx];
+}
+
+int launch_check() {
+  const cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : static_cast<int>(e);
+}
+
+// ------------------------------------------------------------------------------------------ allocation
+struct Bump {
+  ccb_ctx* c;
+  char* cur = nullptr;
+  size_t left = 0;
+  bool ok = true;
+  void* take(size_t bytes) {
+    bytes = (bytes + 255) & ~static_cast<size_t>(255);
+    if (bytes > left) {
+      const size_t chunk = std::max(bytes, static_cast<size_t>(256) << 20);
+      void* p = nullptr;
+      if (cudaMalloc(&p, chunk) != cudaSuccess) {
+        ok = false;
+        cudaGetLastError();
+        return nullptr;
+      }
+      c->allocs.push_back(p);
+      c->alloc_sizes.push_back(chunk);
+      c->device_bytes += static_cast<int64_t>(chunk);
+      cur = static_cast<char*>(p);
+      left = chunk;
+    }
+    void* r = cur;
+    cur += bytes;
+    left -= bytes;
+    return r;
+  }
+  template <typename T>
+  T* arr(size_t n) { return static_cast<T*>(take(n * sizeof(T))); }
+};
+
+void add_slot(ccb_ctx* c, const std::string& name, WeightSlot::Kind kind, void* dst, long long rows, long long cols,
+              long long dst_ld, bool* flag = nullptr, bool optional = false) {
+  WeightSlot s;
+  s.kind = kind;
+  s.dst = dst;
+  s.rows = rows;
+  s.cols = cols;
+  s.dst_ld = dst_ld;
+  s.flag = flag;
+  s.optional = optional;
+  c->slots[name] = s;
+}
+
+void make_linear(ccb_ctx* c, Bump& a, Linear& L, int features, int K, bool bias) {
+  L.features = features;
+  L.K = K;
+  L.w = a.arr<bf16>(static_cast<size_t>(features) * K);
+  L.bias = a.arr<float>(features);
+  L.has_bias = bias;
+  (void)c;
+}
+void make_ln(Bump& a, LayerNormW& n, int d) {
+  n.g = a.arr<float>(d);
+  n.b = a.arr<float>(d);
+}
+
+std::string fmt(const char* f, ...) {
+  char buf[256];
+  va_list ap;
+  va_start(ap, f);
+  vsnprintf(buf, sizeof(buf), f, ap);
+  va_end(ap);
+  return buf;
+}
+
+// matrix [features, K] given as nn.Linear [out, in]
+void slot_linear(ccb_ctx* c, const std::string& base, Linear& L, bool bias_optional = false) {
+  add_slot(c, base + ".weight", WeightSlot::MATRIX, L.w, L.features, L.K, L.K);
+  if (L.has_bias || bias_optional)
+    add_slot(c, base + ".bias", WeightSlot::VECTOR_F32, L.bias, L.features, 1, 1, &L.has_bias, bias_optional && !L.has_bias);
+}
+// HF Conv1D [in, out] -> transposed on ingestion
+void slot_conv1d(ccb_ctx* c, const std::string& base, Linear& L) {
+  add_slot(c, base + ".weight", WeightSlot::MATRIX_T, L.w, L.K, L.features, L.K);
+  add_slot(c, base + ".bias", WeightSlot::VECTOR_F32, L.bias, L.features, 1, 1);
+}
+void slot_ln(ccb_ctx* c, const std::string& base, LayerNormW& n, int d) {
+  add_slot(c, base + ".weight", WeightSlot::VECTOR_F32, n.g, d, 1, 1);
+  add_slot(c, base + ".bias", WeightSlot::VECTOR_F32, n.b, d, 1, 1);
+}
+
+int act_code(int a) { return a; }  // CCB_ACT_* == ccb::Act
+
+// ------------------------------------------------------------------------------------------ forward pieces
+int linear(ccb_ctx* c, const bf16* act, long long lda, int tokens, const Linear& L, int act_fn, const float* residual,
+           long long ldr, void* out, long long ldo, int out_bf16, cudaStream_t s) {
+  GemmArgs g;
+  g.act = act;
+  g.lda = lda;
+  g.tokens = tokens;
+  g.weight = L.w;
+  g.features = L.features;
+  g.K = L.K;
+  g.bias = L.has_bias ? L.bias : nullptr;
+  g.act_fn = act_fn;
+  g.residual = residual;
+  g.ldr = ldr;
+  g.out = out;
+  g.ldo = ldo;
+  g.out_bf16 = out_bf16;
+  return gemm_launch(g, c->gemm_ws, s);
+}
+
+struct BlockShape {
+  int d, hidden, act;
+  float eps;
+  bool parallel;  // GPT-J: attn and mlp both read ln_1(h)
+};
+
+// one pre-LN block on the residual stream c->h [M, d]; `attn` maps c->qkv [M, 3d] -> c->att [M, d]
+template <class AttnFn>
+int block_forward(ccb_ctx* c, const Block& b, int M, const BlockShape& sh, AttnFn attn, cudaStream_t s) {
+  const int d = sh.d;
+  RUN(layernorm_f32_bf16(c->h, d, b.ln1.g, b.ln1.b, sh.eps, c->x, d, M, d, s));
+  RUN(linear(c, c->x, d, M, b.qkv, CCB_ACT_NONE, nullptr, 0, c->qkv, 3 * d, 1, s));
+  RUN(attn());
+  RUN(linear(c, c->att, d, M, b.proj, CCB_ACT_NONE, c->h, d, c->h, d, 0, s));
+  if (!sh.parallel) RUN(layernorm_f32_bf16(c->h, d, b.ln2.g, b.ln2.b, sh.eps, c->x, d, M, d, s));
+  RUN(linear(c, c->x, d, M, b.fc, sh.act, nullptr, 0, c->mlp, sh.hidden, 1, s));
+  RUN(linear(c, c->mlp, sh.hidden, M, b.fc2, CCB_ACT_NONE, c->h, d, c->h, d, 0, s));
+  return 0;
+}
+
+int vit_forward(ccb_ctx* c, const void* images, int dtype, int B, float* feat_out, cudaStream_t s) {
+  const ccb_model_desc& D = c->desc;
+  if (!D.vit_present) return fail(c, "context was created without an image encoder");
+  if (B <= 0 || B > D.max_images) return fail(c, "vit_encode: B=%d outside [1, max_images=%d]", B, D.max_images);
+  const int g = D.vit_image / D.vit_patch, np = g * g, w = D.vit_width, S = np + 1, M = B * S;
+  const int kdim = 3 * D.vit_patch * D.vit_patch;
+  RUN(vit_patchify(images, dtype, B, 3, D.vit_image, D.vit_image, D.vit_patch, c->patches, s));
+  RUN(linear(c, c->patches, kdim, B * np, c->vit_conv, CCB_ACT_NONE, nullptr, 0, c->patch_emb, w, 0, s));
+  RUN(vit_assemble_lnpre(c->patch_emb, c->vit_cls, c->vit_pos, c->vit_ln_pre.g, c->vit_ln_pre.b, 1e-5f, c->h, B, np, w, s));
+  BlockShape sh{w, 4 * w, CCB_ACT_QUICKGELU, 1e-5f, false};
+  const int H = D.vit_heads, hd = w / H;
+  const float scale = 1.0f / sqrtf(static_cast<float>(hd));
+  for (int l = 0; l < D.vit_layers; ++l) {
+    auto attn = [&]() {
+      return attention_prefill(c->qkv, c->att, B, S, H, hd, scale, 0, nullptr, 0, nullptr, 0, 0, nullptr, s);
+    };
+    if (block_forward(c, c->vit[l], M, sh, attn, s)) return -1;
+  }
+  // ln_post(x[:, 0, :]) @ proj
+  RUN(layernorm_f32_bf16(c->h, static_cast<long long>(S) * w, c->vit_ln_post.g, c->vit_ln_post.b, 1e-5f, c->x, w, B, w, s));
+  RUN(linear(c, c->x, w, B, c->vit_proj, CCB_ACT_NONE, nullptr, 0, feat_out, D.vit_out, 0, s));
+  return 0;
+}
+
+// feat [B, dim_clip] f32 -> out [B, out_rows_per_image, d] rows [0, P) (out_rows_per_image >= P)
+int map_forward(ccb_ctx* c, const float* feat, int B, float* out, int out_rows_per_image, cudaStream_t s) {
+  const ccb_model_desc& D = c->desc;
+  if (D.map_kind == CCB_MAP_NONE) return fail(c, "context was created without a prefix mapper");
+  if (B <= 0 || B > D.max_images) return fail(c, "map_prefix: B=%d outside [1, max_images=%d]", B, D.max_images);
+  const int d = D.lm_d, P = D.map_prefix_len, dc = D.map_dim_clip;
+  RUN(cast_f32_bf16(feat, dc, c->feat_bf16, dc, B, dc, s));
+  if (D.map_kind == CCB_MAP_MLP) {
+    // upstream ClipCap MLP mapper: Linear(dc, d*P/2) -> Tanh -> Linear(d*P/2, d*P), viewed as [B, P, d]
+    RUN(linear(c, c->feat_bf16, dc, B, c->map_linear, CCB_ACT_TANH, nullptr, 0, c->mlp, D.map_hidden, 1, s));
+    RUN(linear(c, c->mlp, D.map_hidden, B, c->map_mlp2, CCB_ACT_NONE, nullptr, 0, out,
+               static_cast<long long>(out_rows_per_image) * d, 0, s));
+    return 0;
+  }
+  const int CL = D.map_clip_len, S = CL + P, M = B * S;
+  // linear(x).view(B, clip_len, d) lands in rows [0, clip_len) of every sequence (row pitch S*d);
+  // rows [clip_len, S) are the learned prefix_const (layers/Transformer.py:154-157)
+  RUN(linear(c, c->feat_bf16, dc, B, c->map_linear, CCB_ACT_NONE, nullptr, 0, c->h, static_cast<long long>(S) * d, 0, s));
+  RUN(mapper_fill_const(c->map_prefix_const, c->h, B, CL, P, d, s));
+  BlockShape sh{d, D.map_hidden, act_code(D.map_act), 1e-5f, false};
+  const int H = D.map_heads, hd = d / H;
+  const float scale = 1.0f / sqrtf(static_cast<float>(hd));
+  for (int l = 0; l < D.map_layers; ++l) {
+    auto attn = [&]() {
+      return attention_prefill(c->qkv, c->att, B, S, H, hd, scale, 0, nullptr, 0, nullptr, 0, 0, nullptr, s);
+    };
+    if (block_forward(c, c->mapper[l], M, sh, attn, s)) return -1;
+  }
+  // out = x[:, clip_len:]  (layers/Transformer.py:159)
+  regroup_rows_kernel<<<B * P, 256, 0, s>>>(c->h, P, S, CL, out, out_rows_per_image, d);
+  RUN(launch_check());
+  return 0;
+}
+
+BlockShape lm_shape(const ccb_model_desc& D) {
+  return BlockShape{D.lm_d, 4 * D.lm_d, CCB_ACT_GELU_NEW, D.lm_ln_eps, D.lm_arch == CCB_LM_GPTJ};
+}
+
+// prefill / teacher-forced pass over embeds [B, S, d]; leaves the final residual stream in c->h
+int lm_prefill_layers(ccb_ctx* c, const float* embeds, int B, int S, const uint8_t* key_mask, bool write_cache,
+                      cudaStream_t s) {
+  const ccb_model_desc& D = c->desc;
+  const int d = D.lm_d, M = B * S, H = D.lm_heads, hd = d / H;
+  RUN(add_positions(embeds, D.lm_arch == CCB_LM_GPT2 ? c->wpe : nullptr, 0, S, c->h, M, d, s));
+  const BlockShape sh = lm_shape(D);
+  const float scale = 1.0f / sqrtf(static_cast<float>(hd));
+  for (int l = 0; l < D.lm_layers; ++l) {
+    auto attn = [&]() {
+      return attention_prefill(c->qkv, c->att, B, S, H, hd, scale, 1, write_cache ? &c->kv : nullptr, l,
+                               c->block_table_prefill, 0, D.lm_rotary_dim, key_mask, s);
+    };
+    if (block_forward(c, c->lm[l], M, sh, attn, s)) return -1;
+  }
+  return 0;
+}
+
+// ln_f + lm_head over rows of c->h: all B*S rows, or only the last position of every sequence
+int lm_logits(ccb_ctx* c, int B, int S, int last_only, float* logits_out, int64_t ld, cudaStream_t s) {
+  const ccb_model_desc& D = c->desc;
+  const int d = D.lm_d;
+  if (last_only) {
+    RUN(layernorm_f32_bf16(c->h + static_cast<long long>(S - 1) * d, static_cast<long long>(S) * d, c->lm_lnf.g,
+                           c->lm_lnf.b, D.lm_ln_eps, c->x, d, B, d, s));
+    RUN(linear(c, c->x, d, B, c->lm_head, CCB_ACT_NONE, nullptr, 0, logits_out, ld, 0, s));
+  } else {
+    RUN(layernorm_f32_bf16(c->h, d, c->lm_lnf.g, c->lm_lnf.b, D.lm_ln_eps, c->x, d, B * S, d, s));
+    RUN(linear(c, c->x, d, B * S, c->lm_head, CCB_ACT_NONE, nullptr, 0, logits_out, ld, 0, s));
+  }
+  return 0;
+}
+
+// one token per row: embeds next_tokens at position ctx_len, runs all layers against the paged KV cache
+int lm_decode_step(ccb_ctx* c, int rows, cudaStream_t s) {
+  const ccb_model_desc& D = c->desc;
+  const int d = D.lm_d, H = D.lm_heads, hd = d / H;
+  RUN(embed_tokens(c->wte, D.lm_arch == CCB_LM_GPT2 ? c->wpe : nullptr, c->next_tokens, c->ctx_len, c->h, rows, d, s));
+  const BlockShape sh = lm_shape(D);
+  const float scale = 1.0f / sqrtf(static_cast<float>(hd));
+  for (int l = 0; l < D.lm_layers; ++l) {
+    auto attn = [&]() {
+      return attention_decode(c->qkv, c->att, rows, H, hd, scale, &c->kv, l, c->block_table, c->ctx_len,
+                              D.lm_rotary_dim, s);
+    };
+    if (block_forward(c, c->lm[l], rows, sh, attn, s)) return -1;
+  }
+  RUN(layernorm_f32_bf16(c->h, d, c->lm_lnf.g, c->lm_lnf.b, D.lm_ln_eps, c->x, d, rows, d, s));
+  RUN(linear(c, c->x, d, rows, c->lm_head, CCB_ACT_NONE, nullptr, 0, c->logits, c->ldv, 0, s));
+  return 0;
+}
+
+SampleParams sample_params(ccb_ctx* c, const ccb_gen_params* p, int rows) {
+  SampleParams sp;
+  sp.temperature = p->temperature;
+  sp.top_p = p->top_p;
+  sp.top_k = p->top_k;
+  sp.top_p_rows = p->top_p_rows;
+  sp.top_k_rows = p->top_k_rows;
+  sp.repetition_penalty = p->repetition_penalty;
+  sp.q_noise = p->q_noise;
+  sp.ldq = p->q_ld;
+  sp.q_step_stride = static_cast<long long>(rows) * p->q_ld;
+  sp.seed = p->seed;
+  sp.row_ids = reinterpret_cast<const long long*>(p->row_ids);
+  (void)c;
+  return sp;
+}
+
+// token selection for one step of the greedy / sampling loops on c->logits -> c->next_tokens + bookkeeping
+int select_step(ccb_ctx* c, const ccb_gen_params* p, int rows, int T, bool after_prefill, cudaStream_t s) {
+  const int V = c->desc.lm_vocab;
+  if (p->mode == CCB_GEN_GREEDY) {
+    RUN(sample_greedy(c->logits, c->ldv, rows, V, c->next_tokens, s));
+  } else {
+    SampleParams sp = sample_params(c, p, rows);
+    sp.history = c->gen_tokens;
+    sp.ld_hist = T;
+    sp.hist_len_from_step = 1;
+    sp.step = c->step;
+    RUN(sample_top_p(c->logits, c->ldv, rows, V, sp, c->next_tokens, s));
+  }
+  RUN(advance_rows(c->next_tokens, rows, c->gen_tokens, T, c->lengths, c->stops, c->finished,
+                   after_prefill ? nullptr : c->ctx_len, c->step, p->stop_token, p->max_stops, p->eos_token, s));
+  return 0;
+}
+
+int beam_select(ccb_ctx* c, const ccb_gen_params* p, int N, int T, bool first, cudaStream_t s) {
+  const int beam = p->beam_size, rows = N * beam;
+  if (!first) RUN(increment_rows(c->ctx_len, rows, c->step, s));
+  BeamState st;
+  st.scores = c->scores;
+  st.seq_lengths = c->seq_lengths;
+  st.has_stopped = c->has_stopped;
+  st.tokens = c->gen_tokens;
+  st.max_len = T;
+  st.step = c->step;
+  RUN(beam_step(c->logits, c->ldv, N, beam, c->desc.lm_vocab, p->temperature, p->stop_token, st, c->next_tokens,
+                c->src_rows, c->block_table, c->max_pages_per_row, c->ctx_len, s));
+  return 0;
+}
+
+int decode_iteration(ccb_ctx* c, const ccb_gen_params* p, int N, int rows, int T, cudaStream_t s) {
+  if (lm_decode_step(c, rows, s)) return -1;
+  if (p->mode == CCB_GEN_BEAM) return beam_select(c, p, N, T, false, s);
+  return select_step(c, p, rows, T, false, s);
+}
+
+std::string graph_key(const ccb_gen_params* p, int N, int rows, int T) {
+  char buf[512];
+  snprintf(buf, sizeof(buf), "m%d N%d r%d T%d st%d ms%d eos%d t%a p%a k%d rp%a b%d seed%llu q%p ld%lld ids%p pr%p kr%p",
+           p->mode, N, rows, T, p->stop_token, p->max_stops, p->eos_token, p->temperature, p->top_p, p->top_k,
+           p->repetition_penalty, p->beam_size, static_cast<unsigned long long>(p->seed),
+           static_cast<const void*>(p->q_noise), static_cast<long long>(p->q_ld), static_cast<const void*>(p->row_ids),
+           static_cast<const void*>(p->top_p_rows), static_cast<const void*>(p->top_k_rows));
+  return buf;
+}
+
+int generate_on_work_stream(ccb_ctx* c, const ccb_gen_params* p, const float* embeds, int N, int S0,
+                            int32_t* tokens_out, int32_t* lengths_out, float* scores_out) {
+  const ccb_model_desc& D = c->desc;
+  cudaStream_t s = c->work;
+  const bool is_beam = p->mode == CCB_GEN_BEAM;
+  const int beam = is_beam ? p->beam_size : 1;
+  const int rows = N * beam;
+  const int T = p->max_new_tokens;
+  if (p->mode != CCB_GEN_GREEDY && p->mode != CCB_GEN_SAMPLE && !is_beam) return fail(c, "generate: unknown mode %d", p->mode);
+  if (N <= 0 || N > D.max_images) return fail(c, "generate: N=%d outside [1, max_images=%d]", N, D.max_images);
+  if (beam < 1 || beam > D.max_beam || beam > 8) return fail(c, "generate: beam_size=%d outside [1, max_beam=%d]", beam, D.max_beam);
+  if (T <= 0 || S0 <= 0 || S0 + T > D.max_ctx) return fail(c, "generate: S0=%d + max_new_tokens=%d exceeds max_ctx=%d", S0, T, D.max_ctx);
+  if (N * S0 > D.max_lm_tokens) return fail(c, "generate: N*S0=%d exceeds max_lm_tokens=%d", N * S0, D.max_lm_tokens);
+  if (S0 > 256) return fail(c, "generate: prefix longer than 256 tokens is not supported");
+
+  // KV pool geometry for this call
+  const int page_tokens = is_beam ? 1 : D.page_tokens;
+  const int pages_per_row = is_beam ? (S0 + T) : (S0 + T + page_tokens - 1) / page_tokens;
+  const long long need_tokens = is_beam ? static_cast<long long>(N) * (S0 + static_cast<long long>(beam) * T)
+                                        : static_cast<long long>(rows) * pages_per_row * page_tokens;
+  if (need_tokens > c->kv_pool_tokens) return fail(c, "generate: KV pool too small (%lld > %lld tokens)", need_tokens, c->kv_pool_tokens);
+  c->kv.page_tokens = page_tokens;
+  c->kv.num_pages = static_cast<int>(c->kv_pool_tokens / page_tokens);
+  c->kv.max_pages_per_row = c->max_pages_per_row;
+
+  init_state_kernel<<<148, 256, 0, s>>>(c->block_table, c->block_table_prefill, c->max_pages_per_row, rows, N, beam, S0,
+                                        T, page_tokens, pages_per_row, c->ctx_len, c->step, c->lengths, c->stops,
+                                        c->finished, c->scores, c->seq_lengths, c->has_stopped);
+  RUN(launch_check());
+  CUDA_OK(cudaMemsetAsync(c->gen_tokens, 0, sizeof(int) * static_cast<size_t>(rows) * T, s));
+
+  CUDA_OK(cudaEventRecord(c->ev_t0, s));
+  // ---- prefill: one pass over the prefix, K/V written to the cache, logits of the last position
+  if (lm_prefill_layers(c, embeds, N, S0, nullptr, true, s)) return -1;
+  if (lm_logits(c, N, S0, 1, c->logits, c->ldv, s)) return -1;
+  if (is_beam) {
+    if (beam_select(c, p, N, T, true, s)) return -1;
+  } else {
+    if (select_step(c, p, rows, T, true, s)) return -1;
+  }
+  CUDA_OK(cudaEventRecord(c->ev_t1, s));
+
+  // ---- decode: T-1 replays of one captured step (every kernel reads step / ctx_len from device memory)
+  if (T > 1) {
+    const std::string key = graph_key(p, N, rows, T);
+    auto it = c->graphs.find(key);
+    if (it == c->graphs.end()) {
+      cudaGraph_t graph = nullptr;
+      CUDA_OK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+      c->capturing = true;
+      c->capture_launches = 0;
+      const int r = decode_iteration(c, p, N, rows, T, s);
+      c->capturing = false;
+      const cudaError_t e = cudaStreamEndCapture(s, &graph);
+      if (r != 0) {
+        if (graph) cudaGraphDestroy(graph);
+        return -1;
+      }
+      if (e != cudaSuccess) return fail(c, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+      GraphEntry ge;
+      ge.nodes = c->capture_launches;
+      const cudaError_t e2 = cudaGraphInstantiate(&ge.exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (e2 != cudaSuccess) return fail(c, "cudaGraphInstantiate: %s", cudaGetErrorString(e2));
+      if (c->graphs.size() >= 32) {  // bound the cache
+        for (auto& kvp : c->graphs) cudaGraphExecDestroy(kvp.second.exec);
+        c->graphs.clear();
+      }
+      it = c->graphs.emplace(key, ge).first;
+    }
+    for (int t = 1; t < T; ++t) {
+      CUDA_OK(cudaGraphLaunch(it->second.exec, s));
+      c->launches += it->second.nodes;
+    }
+  }
+  CUDA_OK(cudaEventRecord(c->ev_t2, s));
+  c->last_decode_steps = T - 1;
+  c->timing_valid = true;
+
+  // ---- results
+  CUDA_OK(cudaMemcpyAsync(tokens_out, c->gen_tokens, sizeof(int) * static_cast<size_t>(rows) * T, cudaMemcpyDeviceToDevice, s));
+  if (is_beam) {
+    finalize_beam_kernel<<<(rows + 255) / 256, 256, 0, s>>>(c->scores, c->seq_lengths, rows, lengths_out, scores_out);
+    RUN(launch_check());
+  } else if (lengths_out) {
+    CUDA_OK(cudaMemcpyAsync(lengths_out, c->lengths, sizeof(int) * rows, cudaMemcpyDeviceToDevice, s));
+  }
+  return 0;
+}
+
+int fence_in(ccb_ctx* c, cudaStream_t caller) {
+  CUDA_OK(cudaEventRecord(c->ev_in, caller));
+  CUDA_OK(cudaStreamWaitEvent(c->work, c->ev_in, 0));
+  return 0;
+}
+int fence_out(ccb_ctx* c, cudaStream_t caller) {
+  CUDA_OK(cudaEventRecord(c->ev_out, c->work));
+  CUDA_OK(cudaStreamWaitEvent(caller, c->ev_out, 0));
+  return 0;
+}
+
+bool starts_with(const char* s, const char* prefix, const char** rest) {
+  const size_t n = strlen(prefix);
+  if (strncmp(s, prefix, n) == 0) {
+    *rest = s + n;
+    return true;
+  }
+  return false;
+}
+
+}  // namespace
+
+// ================================================================================================ C ABI
+extern "C" {
+
+const char* ccb_last_error(const ccb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err; }
+
+int64_t ccb_device_bytes(const ccb_ctx* ctx) { return ctx ? ctx->device_bytes : 0; }
+int64_t ccb_launch_count(const ccb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+void ccb_destroy(ccb_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  for (auto& kvp : c->graphs) cudaGraphExecDestroy(kvp.second.exec);
+  for (void* p : c->allocs) cudaFree(p);
+  if (c->work) cudaStreamDestroy(c->work);
+  for (cudaEvent_t e : {c->ev_in, c->ev_out, c->ev_t0, c->ev_t1, c->ev_t2})
+    if (e) cudaEventDestroy(e);
+  delete c;
+}
+
+int ccb_create(ccb_ctx** out, const ccb_model_desc* desc, int device) {
+  if (!out || !desc) return fail(nullptr, "ccb_create: null argument");
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(nullptr, "ccb_create: no CUDA device (this library has no CPU fallback)");
+  }
+  if (device < 0 || device >= ndev) return fail(nullptr, "ccb_create: device %d out of range (%d devices)", device, ndev);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(nullptr, "ccb_create: cudaGetDeviceProperties failed");
+  if (prop.major != 10) return fail(nullptr, "ccb_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+  if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, "ccb_create: cudaSetDevice failed");
+
+  const ccb_model_desc& D = *desc;
+  if (D.lm_d <= 0 || D.lm_layers <= 0 || D.lm_heads <= 0 || D.lm_vocab <= 0 || D.lm_d % D.lm_heads)
+    return fail(nullptr, "ccb_create: bad language-model dimensions");
+  if (D.lm_d % 64) return fail(nullptr, "ccb_create: lm_d must be a multiple of 64");
+  const int lm_hd = D.lm_d / D.lm_heads;
+  if (lm_hd != 64 && lm_hd != 128 && lm_hd != 256) return fail(nullptr, "ccb_create: LM head_dim %d unsupported (64/128/256)", lm_hd);
+  if (D.lm_arch != CCB_LM_GPT2 && D.lm_arch != CCB_LM_GPTJ) return fail(nullptr, "ccb_create: unknown lm_arch");
+  if (D.max_images <= 0 || D.max_beam <= 0 || D.max_ctx <= 0 || D.max_lm_tokens <= 0 || D.page_tokens <= 0)
+    return fail(nullptr, "ccb_create: capacities must be positive");
+  if (D.map_kind == CCB_MAP_TRANSFORMER && (D.map_heads <= 0 || D.lm_d % D.map_heads || (D.lm_d / D.map_heads) % 2 ||
+                                            D.map_hidden % 64 || D.map_dim_clip % 64))
+    return fail(nullptr, "ccb_create: bad mapper dimensions");
+  if (D.map_kind == CCB_MAP_MLP && (D.map_hidden % 64 || D.map_dim_clip % 64)) return fail(nullptr, "ccb_create: bad MLP mapper dimensions");
+  if (D.vit_present && (D.vit_width % 64 || D.vit_width % D.vit_heads || D.vit_image % D.vit_patch || D.vit_patch % 8))
+    return fail(nullptr, "ccb_create: bad ViT dimensions");
+
+  ccb_ctx* c = new ccb_ctx();
+  c->desc = D;
+  c->device = device;
+  c->num_sms = prop.multiProcessorCount;
+  if (gemm_init(device) != 0) {
+    fail(nullptr, "ccb_create: %s", gemm_last_error());
+    delete c;
+    return -1;
+  }
+  Bump a{c};
+  const int d = D.lm_d, V = D.lm_vocab;
+
+  // ---- language model
+  c->wte = a.arr<bf16>(static_cast<size_t>(V) * d);
+  add_slot(c, "transformer.wte.weight", WeightSlot::ROWS_BF16, c->wte, V, d, d);
+  if (D.lm_arch == CCB_LM_GPT2) {
+    c->wpe = a.arr<bf16>(static_cast<size_t>(D.lm_n_pos) * d);
+    add_slot(c, "transformer.wpe.weight", WeightSlot::ROWS_BF16, c->wpe, D.lm_n_pos, d, d);
+  }
+  c->lm.resize(D.lm_layers);
+  for (int l = 0; l < D.lm_layers; ++l) {
+    Block& b = c->lm[l];
+    const std::string base = fmt("transformer.h.%d", l);
+    make_ln(a, b.ln1, d);
+    slot_ln(c, base + ".ln_1", b.ln1, d);
+    if (D.lm_arch == CCB_LM_GPT2) {
+      make_ln(a, b.ln2, d);
+      slot_ln(c, base + ".ln_2", b.ln2, d);
+      make_linear(c, a, b.qkv, 3 * d, d, true);
+      make_linear(c, a, b.proj, d, d, true);
+      make_linear(c, a, b.fc, 4 * d, d, true);
+      make_linear(c, a, b.fc2, d, 4 * d, true);
+      slot_conv1d(c, base + ".attn.c_attn", b.qkv);
+      slot_conv1d(c, base + ".attn.c_proj", b.proj);
+      slot_conv1d(c, base + ".mlp.c_fc", b.fc);
+      slot_conv1d(c, base + ".mlp.c_proj", b.fc2);
+    } else {
+      make_linear(c, a, b.qkv, 3 * d, d, false);
+      make_linear(c, a, b.proj, d, d, false);
+      make_linear(c, a, b.fc, 4 * d, d, true);
+      make_linear(c, a, b.fc2, d, 4 * d, true);
+      add_slot(c, base + ".attn.q_proj.weight", WeightSlot::MATRIX, b.qkv.w, d, d, d);
+      add_slot(c, base + ".attn.k_proj.weight", WeightSlot::MATRIX, b.qkv.w + static_cast<size_t>(d) * d, d, d, d);
+      add_slot(c, base + ".attn.v_proj.weight", WeightSlot::MATRIX, b.qkv.w + 2 * static_cast<size_t>(d) * d, d, d, d);
+      slot_linear(c, base + ".attn.out_proj", b.proj);
+      slot_linear(c, base + ".mlp.fc_in", b.fc);
+      slot_linear(c, base + ".mlp.fc_out", b.fc2);
+    }
+  }
+  make_ln(a, c->lm_lnf, d);
+  slot_ln(c, "transformer.ln_f", c->lm_lnf, d);
+  if (D.lm_arch == CCB_LM_GPT2) {
+    c->lm_head.w = c->wte;  // tied
+    c->lm_head.features = V;
+    c->lm_head.K = d;
+    c->lm_head.has_bias = false;
+  } else {
+    make_linear(c, a, c->lm_head, V, d, true);
+    slot_linear(c, "lm_head", c->lm_head);
+  }
+
+  // ---- mapper
+  int map_S = 0;
+  if (D.map_kind == CCB_MAP_TRANSFORMER) {
+    map_S = D.map_clip_len + D.map_prefix_len;
+    make_linear(c, a, c->map_linear, D.map_clip_len * d, D.map_dim_clip, true);
+    slot_linear(c, "clip_project.linear", c->map_linear);
+    c->map_prefix_const = a.arr<float>(static_cast<size_t>(D.map_prefix_len) * d);
+    add_slot(c, "clip_project.prefix_const", WeightSlot::VECTOR_F32, c->map_prefix_const,
+             static_cast<long long>(D.map_prefix_len) * d, 1, 1);
+    c->mapper.resize(D.map_layers);
+    for (int l = 0; l < D.map_layers; ++l) {
+      Block& b = c->mapper[l];
+      const std::string base = fmt("clip_project.transformer.layers.%d", l);
+      make_ln(a, b.ln1, d);
+      make_ln(a, b.ln2, d);
+      slot_ln(c, base + ".norm1", b.ln1, d);
+      slot_ln(c, base + ".norm2", b.ln2, d);
+      make_linear(c, a, b.qkv, 3 * d, d, false);
+      make_linear(c, a, b.proj, d, d, true);
+      make_linear(c, a, b.fc, D.map_hidden, d, true);
+      make_linear(c, a, b.fc2, d, D.map_hidden, true);
+      // to_queries [d, d] -> rows [0, d); to_keys_values [2d, d] -> rows [d, 3d): keys then values
+      // (layers/MultiHeadAttention.py:24-30).  The projections are bias-free by default (Transformer.py:91,96).
+      add_slot(c, base + ".attn.to_queries.weight", WeightSlot::MATRIX, b.qkv.w, d, d, d);
+      add_slot(c, base + ".attn.to_keys_values.weight", WeightSlot::MATRIX, b.qkv.w + static_cast<size_t>(d) * d, 2 * d, d, d);
+      add_slot(c, base + ".attn.to_queries.bias", WeightSlot::VECTOR_F32, b.qkv.bias, d, 1, 1, &b.qkv.has_bias, true);
+      add_slot(c, base + ".attn.to_keys_values.bias", WeightSlot::VECTOR_F32, b.qkv.bias + d, 2 * d, 1, 1, &b.qkv.has_bias, true);
+      slot_linear(c, base + ".attn.project", b.proj);
+      slot_linear(c, base + ".mlp.fc1", b.fc);
+      slot_linear(c, base + ".mlp.fc2", b.fc2);
+    }
+  } else if (D.map_kind == CCB_MAP_MLP) {
+    make_linear(c, a, c->map_linear, D.map_hidden, D.map_dim_clip, true);
+    make_linear(c, a, c->map_mlp2, D.map_prefix_len * d, D.map_hidden, true);
+    slot_linear(c, "clip_project.model.0", c->map_linear);
+    slot_linear(c, "clip_project.model.2", c->map_mlp2);
+  }
+
+  // ---- ViT
+  int vit_S = 0;
+  if (D.vit_present) {
+    const int w = D.vit_width, g = D.vit_image / D.vit_patch, np = g * g, kdim = 3 * D.vit_patch * D.vit_patch;
+    vit_S = np + 1;
+    make_linear(c, a, c->vit_conv, w, kdim, false);
+    add_slot(c, "visual.conv1.weight", WeightSlot::MATRIX, c->vit_conv.w, w, kdim, kdim);
+    c->vit_cls = a.arr<float>(w);
+    c->vit_pos = a.arr<float>(static_cast<size_t>(vit_S) * w);
+    add_slot(c, "visual.class_embedding", WeightSlot::VECTOR_F32, c->vit_cls, w, 1, 1);
+    add_slot(c, "visual.positional_embedding", WeightSlot::VECTOR_F32, c->vit_pos, static_cast<long long>(vit_S) * w, 1, 1);
+    make_ln(a, c->vit_ln_pre, w);
+    make_ln(a, c->vit_ln_post, w);
+    slot_ln(c, "visual.ln_pre", c->vit_ln_pre, w);
+    slot_ln(c, "visual.ln_post", c->vit_ln_post, w);
+    c->vit.resize(D.vit_layers);
+    for (int l = 0; l < D.vit_layers; ++l) {
+      Block& b = c->vit[l];
+      const std::string base = fmt("visual.transformer.resblocks.%d", l);
+      make_ln(a, b.ln1, w);
+      make_ln(a, b.ln2, w);
+      slot_ln(c, base + ".ln_1", b.ln1, w);
+      slot_ln(c, base + ".ln_2", b.ln2, w);
+      make_linear(c, a, b.qkv, 3 * w, w, true);
+      make_linear(c, a, b.proj, w, w, true);
+      make_linear(c, a, b.fc, 4 * w, w, true);
+      make_linear(c, a, b.fc2, w, 4 * w, true);
+      add_slot(c, base + ".attn.in_proj_weight", WeightSlot::MATRIX, b.qkv.w, 3 * w, w, w);
+      add_slot(c, base + ".attn.in_proj_bias", WeightSlot::VECTOR_F32, b.qkv.bias, 3 * w, 1, 1);
+      slot_linear(c, base + ".attn.out_proj", b.proj);
+      slot_linear(c, base + ".mlp.c_fc", b.fc);
+      slot_linear(c, base + ".mlp.c_proj", b.fc2);
+    }
+    make_linear(c, a, c->vit_proj, D.vit_out, w, false);
+    add_slot(c, "visual.proj", WeightSlot::MATRIX_T, c->vit_proj.w, w, D.vit_out, w);  // proj [w, out] -> [out, w]
+  }
+
+  // ---- workspaces
+  c->max_rows = D.max_images * D.max_beam;
+  int M = std::max(D.max_lm_tokens, c->max_rows);
+  M = std::max(M, D.max_images * map_S);
+  M = std::max(M, D.max_images * vit_S);
+  c->max_rows_tokens = M;
+  c->dmax = std::max(d, D.vit_present ? D.vit_width : 0);
+  c->hidden_max = std::max(4 * d, std::max(D.map_kind != CCB_MAP_NONE ? D.map_hidden : 0, D.vit_present ? 4 * D.vit_width : 0));
+  const size_t Mz = static_cast<size_t>(M);
+  c->h = a.arr<float>(Mz * c->dmax);
+  c->x = a.arr<bf16>(Mz * c->dmax);
+  c->qkv = a.arr<bf16>(Mz * 3 * c->dmax);
+  c->att = a.arr<bf16>(Mz * c->dmax);
+  c->mlp = a.arr<bf16>(Mz * c->hidden_max);
+  if (D.vit_present) {
+    const int g = D.vit_image / D.vit_patch, np = g * g, kdim = 3 * D.vit_patch * D.vit_patch;
+    c->patches = a.arr<bf16>(static_cast<size_t>(D.max_images) * np * kdim);
+    c->patch_emb = a.arr<float>(static_cast<size_t>(D.max_images) * np * D.vit_width);
+  }
+  const int dc = std::max(D.map_dim_clip, D.vit_present ? D.vit_out : 0);
+  c->feat = a.arr<float>(static_cast<size_t>(D.max_images) * std::max(dc, 1));
+  c->feat_bf16 = a.arr<bf16>(static_cast<size_t>(D.max_images) * std::max(dc, 1));
+  c->prefix = a.arr<float>(static_cast<size_t>(D.max_images) * (std::max(D.map_prefix_len, 0) + 1) * d);
+  c->ldv = (static_cast<int64_t>(V) + 63) / 64 * 64;
+  c->logits = a.arr<float>(static_cast<size_t>(std::max(c->max_rows, D.max_images)) * c->ldv);
+  c->gemm_ws.ws_bytes = static_cast<size_t>(96) << 20;
+  c->gemm_ws.ws = static_cast<float*>(a.take(c->gemm_ws.ws_bytes));
+  c->gemm_ws.sem_count = 8192;
+  c->gemm_ws.sem = a.arr<int>(c->gemm_ws.sem_count);
+  c->gemm_ws.num_sms = c->num_sms;
+
+  // ---- KV pool + state
+  const int lm_H = D.lm_heads;
+  c->kv.L = D.lm_layers;
+  c->kv.H = lm_H;
+  c->kv.hd = lm_hd;
+  const long long ctx_round = (static_cast<long long>(D.max_ctx) + D.page_tokens - 1) / D.page_tokens * D.page_tokens;
+  c->kv_pool_tokens = static_cast<long long>(c->max_rows) * ctx_round;
+  c->kv.base = a.arr<bf16>(static_cast<size_t>(2) * D.lm_layers * c->kv_pool_tokens * d);
+  c->max_pages_per_row = D.max_ctx;
+  c->block_table = a.arr<int>(static_cast<size_t>(c->max_rows) * c->max_pages_per_row);
+  c->block_table_prefill = a.arr<int>(static_cast<size_t>(D.max_images) * c->max_pages_per_row);
+  c->ctx_len = a.arr<int>(c->max_rows);
+  c->step = a.arr<int>(1);
+  c->next_tokens = a.arr<int>(c->max_rows);
+  c->src_rows = a.arr<int>(c->max_rows);
+  c->gen_tokens = a.arr<int>(static_cast<size_t>(c->max_rows) * D.max_ctx);
+  c->lengths = a.arr<int>(c->max_rows);
+  c->stops = a.arr<int>(c->max_rows);
+  c->finished = a.arr<uint8_t>(c->max_rows);
+  c->scores = a.arr<float>(c->max_rows);
+  c->seq_lengths = a.arr<float>(c->max_rows);
+  c->has_stopped = a.arr<uint8_t>(c->max_rows);
+  c->bos_token = a.arr<int>(D.max_images);
+
+  if (!a.ok) {
+    fail(nullptr, "ccb_create: out of device memory after %lld bytes", static_cast<long long>(c->device_bytes));
+    ccb_destroy(c);
+    return -1;
+  }
+  // zero everything once (optional biases, semaphores, block tables)
+  for (size_t i = 0; i < c->allocs.size(); ++i) cudaMemset(c->allocs[i], 0, c->alloc_sizes[i]);
+  if (cudaStreamCreateWithFlags(&c->work, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreate(&c->ev_t0) != cudaSuccess || cudaEventCreate(&c->ev_t1) != cudaSuccess ||
+      cudaEventCreate(&c->ev_t2) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
+    fail(nullptr, "ccb_create: stream / event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    ccb_destroy(c);
+    return -1;
+  }
+  *out = c;
+  return 0;
+}
+
+int ccb_load_weight(ccb_ctx* c, const char* name, const void* dev_ptr, int dtype, const int64_t* shape, int ndim,
+                    void* stream) {
+  if (!c || !name || !dev_ptr || !shape) return fail(c, "ccb_load_weight: null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // normalise the reference's module prefixes
+  std::string key;
+  const char* rest = nullptr;
+  if (starts_with(name, "language_model.", &rest)) key = rest;
+  else if (starts_with(name, "visual_encoder.", &rest)) key = std::string("visual.") + rest;
+  else key = name;
+  auto it = c->slots.find(key);
+  if (it == c->slots.end()) return 1;  // not used by this context
+  WeightSlot& w = it->second;
+  long long numel = 1;
+  for (int i = 0; i < ndim; ++i) numel *= shape[i];
+  if (numel != w.rows * w.cols) return fail(c, "ccb_load_weight(%s): expected %lld elements, got %lld", name, w.rows * w.cols, numel);
+  if ((w.kind == WeightSlot::MATRIX || w.kind == WeightSlot::MATRIX_T || w.kind == WeightSlot::ROWS_BF16) && ndim >= 2 &&
+      shape[0] != w.rows)
+    return fail(c, "ccb_load_weight(%s): expected leading dimension %lld, got %lld", name, w.rows, static_cast<long long>(shape[0]));
+  int r = 0;
+  switch (w.kind) {
+    case WeightSlot::MATRIX:
+    case WeightSlot::ROWS_BF16:
+      r = convert_rows_bf16(dev_ptr, dtype, w.rows, static_cast<int>(w.cols), static_cast<bf16*>(w.dst), w.dst_ld, s);
+      break;
+    case WeightSlot::MATRIX_T:
+      r = transpose_bf16(dev_ptr, dtype, static_cast<int>(w.rows), static_cast<int>(w.cols), static_cast<bf16*>(w.dst), w.dst_ld, s);
+      break;
+    case WeightSlot::VECTOR_F32:
+      r = convert_f32(dev_ptr, dtype, w.rows * w.cols, static_cast<float*>(w.dst), s);
+      break;
+  }
+  if (r != 0) return fail(c, "ccb_load_weight(%s): conversion kernel failed: %s", name, cudaGetErrorString(static_cast<cudaError_t>(r)));
+  c->launches++;
+  w.loaded = true;
+  if (w.flag) *w.flag = true;
+  return 0;
+}
+
+int ccb_weights_complete(ccb_ctx* c) {
+  if (!c) return -1;
+  for (auto& kvp : c->slots)
+    if (!kvp.second.loaded && !kvp.second.optional) return fail(c, "weight not loaded: %s", kvp.first.c_str());
+  return 0;
+}
+
+int ccb_vit_encode(ccb_ctx* c, const void* images, int dtype, int B, float* feat_out, void* stream) {
+  if (!c || !images || !feat_out) return fail(c, "ccb_vit_encode: null argument");
+  return vit_forward(c, images, dtype, B, feat_out, static_cast<cudaStream_t>(stream));
+}
+
+int ccb_map_prefix(ccb_ctx* c, const float* feat, int B, float* prefix_out, void* stream) {
+  if (!c || !feat || !prefix_out) return fail(c, "ccb_map_prefix: null argument");
+  return map_forward(c, feat, B, prefix_out, c->desc.map_prefix_len, static_cast<cudaStream_t>(stream));
+}
+
+int ccb_embed_tokens(ccb_ctx* c, const int32_t* tokens, int n, float* out, void* stream) {
+  if (!c || !tokens || !out) return fail(c, "ccb_embed_tokens: null argument");
+  if (n <= 0) return 0;
+  RUN(embed_tokens(c->wte, nullptr, tokens, nullptr, out, n, c->desc.lm_d, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int ccb_lm_forward(ccb_ctx* c, const float* embeds, int B, int S, const uint8_t* key_mask, float* logits_out,
+                   int64_t ld_logits, int last_only, void* stream) {
+  if (!c || !embeds || !logits_out) return fail(c, "ccb_lm_forward: null argument");
+  if (B <= 0 || S <= 0 || static_cast<long long>(B) * S > c->desc.max_lm_tokens)
+    return fail(c, "ccb_lm_forward: B*S=%lld exceeds max_lm_tokens=%d", static_cast<long long>(B) * S, c->desc.max_lm_tokens);
+  if (S > 256) return fail(c, "ccb_lm_forward: S=%d > 256 is not supported", S);
+  if (ld_logits < c->desc.lm_vocab) return fail(c, "ccb_lm_forward: ld_logits < vocab");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (lm_prefill_layers(c, embeds, B, S, key_mask, false, s)) return -1;
+  return lm_logits(c, B, S, last_only, logits_out, ld_logits, s);
+}
+
+int ccb_generate(ccb_ctx* c, const ccb_gen_params* p, const float* embeds, int N, int S0, int32_t* tokens_out,
+                 int32_t* lengths_out, float* scores_out, void* stream) {
+  if (!c || !p || !embeds || !tokens_out) return fail(c, "ccb_generate: null argument");
+  cudaStream_t caller = static_cast<cudaStream_t>(stream);
+  if (fence_in(c, caller)) return -1;
+  const int r = generate_on_work_stream(c, p, embeds, N, S0, tokens_out, lengths_out, scores_out);
+  if (fence_out(c, caller)) return -1;
+  return r;
+}
+
+int ccb_caption_images(ccb_ctx* c, const ccb_gen_params* p, const void* images, int dtype, int N, int append_bos,
+                       int32_t* tokens_out, int32_t* lengths_out, float* scores_out, void* stream) {
+  if (!c || !p || !images || !tokens_out) return fail(c, "ccb_caption_images: null argument");
+  cudaStream_t caller = static_cast<cudaStream_t>(stream);
+  if (fence_in(c, caller)) return -1;
+  cudaStream_t s = c->work;
+  const int P = c->desc.map_prefix_len, d = c->desc.lm_d;
+  const int extra = append_bos >= 0 ? 1 : 0;
+  int r = vit_forward(c, images, dtype, N, c->feat, s);
+  if (r == 0) r = map_forward(c, c->feat, N, c->prefix, P + extra, s);
+  if (r == 0 && extra) {
+    if (append_bos >= c->desc.lm_vocab) {
+      r = fail(c, "ccb_caption_images: BOS id %d outside the vocabulary", append_bos);
+    } else {
+      token_rows_kernel<<<N, 256, 0, s>>>(c->wte, append_bos, c->prefix, static_cast<long long>(P + extra) * d, P, d);
+      const int lc = launch_check();
+      if (lc) r = fail(c, "token_rows_kernel: %s", cudaGetErrorString(static_cast<cudaError_t>(lc)));
+      else c->launches++;
+    }
+  }
+  if (r == 0) r = generate_on_work_stream(c, p, c->prefix, N, P + extra, tokens_out, lengths_out, scores_out);
+  if (fence_out(c, caller)) return -1;
+  return r;
+}
+
+int ccb_last_timing(ccb_ctx* c, float* prefill_ms, float* decode_ms, int* decode_steps) {
+  if (!c) return -1;
+  if (!c->timing_valid) return fail(c, "ccb_last_timing: no generate call yet");
+  float a = 0.f, b = 0.f;
+  CUDA_OK(cudaEventElapsedTime(&a, c->ev_t0, c->ev_t1));
+  CUDA_OK(cudaEventElapsedTime(&b, c->ev_t1, c->ev_t2));
+  if (prefill_ms) *prefill_ms = a;
+  if (decode_ms) *decode_ms = b;
+  if (decode_steps) *decode_steps = c->last_decode_steps;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------- samplers on caller tensors
+int ccb_sample(ccb_ctx* c, const float* logits, int64_t ld, int B, int V, const ccb_gen_params* p,
+               const int32_t* history, int64_t ld_hist, int hist_len, int step, float* filtered_out, int32_t* next_out,
+               int32_t* alt_out, void* stream) {
+  if (!c || !logits || !p || !next_out) return fail(c, "ccb_sample: null argument");
+  SampleParams sp = sample_params(c, p, B);
+  sp.history = history;
+  sp.ld_hist = ld_hist;
+  sp.hist_len_scalar = hist_len;
+  sp.step_scalar = step;
+  sp.filtered_out = filtered_out;
+  sp.alt_out = alt_out;
+  RUN(sample_top_p(logits, ld, B, V, sp, next_out, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int ccb_argmax(ccb_ctx* c, const float* logits, int64_t ld, int B, int V, int32_t* next_out, void* stream) {
+  if (!c || !logits || !next_out) return fail(c, "ccb_argmax: null argument");
+  RUN(sample_greedy(logits, ld, B, V, next_out, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int ccb_beam_step(ccb_ctx* c, const float* logits, int64_t ld, int N, int beam, int V, float temperature,
+                  int stop_token, int step, float* scores, float* seq_lengths, uint8_t* has_stopped, int32_t* tokens,
+                  int max_len, int32_t* next_tokens, int32_t* src_rows, void* stream) {
+  if (!c || !logits || !scores || !seq_lengths || !has_stopped || !tokens || !next_tokens || !src_rows)
+    return fail(c, "ccb_beam_step: null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // the step counter lives in device memory for the graph-replayed loop; stage the caller's value
+  CUDA_OK(cudaMemcpyAsync(c->step, &step, sizeof(int), cudaMemcpyHostToDevice, s));
+  CUDA_OK(cudaStreamSynchronize(s));  // `step` is a stack variable
+  BeamState st;
+  st.scores = scores;
+  st.seq_lengths = seq_lengths;
+  st.has_stopped = has_stopped;
+  st.tokens = tokens;
+  st.max_len = max_len;
+  st.step = c->step;
+  RUN(beam_step(logits, ld, N, beam, V, temperature, stop_token, st, next_tokens, src_rows, nullptr, 0, nullptr, s));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------- single operators
+int ccb_op_linear(ccb_ctx* c, const void* x, int64_t lda, int tokens, const void* w, int features, int K,
+                  const float* bias, int act, const float* residual, int64_t ldr, void* out, int64_t ldo, int out_bf16,
+                  int orientation, int bn, int split_k, void* stream) {
+  if (!c || !x || !w || !out) return fail(c, "ccb_op_linear: null argument");
+  GemmArgs g;
+  g.act = static_cast<const bf16*>(x);
+  g.lda = lda;
+  g.tokens = tokens;
+  g.weight = static_cast<const bf16*>(w);
+  g.features = features;
+  g.K = K;
+  g.bias = bias;
+  g.act_fn = act;
+  g.residual = residual;
+  g.ldr = ldr;
+  g.out = out;
+  g.ldo = ldo;
+  g.out_bf16 = out_bf16;
+  g.force_orientation = orientation;
+  g.force_bn = bn;
+  g.force_split = split_k;
+  RUN(gemm_launch(g, c->gemm_ws, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int ccb_op_layernorm(ccb_ctx* c, const float* x, const float* gamma, const float* beta, float eps, void* y_bf16,
+                     int rows, int d, void* stream) {
+  if (!c || !x || !gamma || !beta || !y_bf16) return fail(c, "ccb_op_layernorm: null argument");
+  RUN(layernorm_f32_bf16(x, d, gamma, beta, eps, static_cast<bf16*>(y_bf16), d, rows, d, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int ccb_op_attention(ccb_ctx* c, const void* qkv_bf16, void* out_bf16, int B, int S, int H, int hd, float scale,
+                     int causal, int rotary_dim, void* stream) {
+  if (!c || !qkv_bf16 || !out_bf16) return fail(c, "ccb_op_attention: null argument");
+  RUN(attention_prefill(static_cast<const bf16*>(qkv_bf16), static_cast<bf16*>(out_bf16), B, S, H, hd, scale, causal,
+                        nullptr, 0, nullptr, 0, rotary_dim, nullptr, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+}  // extern "C"

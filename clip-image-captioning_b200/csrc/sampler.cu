@@ -1,0 +1,720 @@
+// On-device token selection: greedy arg-max, the reference's logit processors (repetition penalty, temperature,
+// top-k, top-p; sampling.py:65-69,114-162 and inference.py:24-57) fused with softmax + multinomial sampling, the
+// beam-search step of inference.py:98-131, and the per-step bookkeeping that lets the whole decode loop run
+// without a host round-trip.
+//
+// Selection without sorting: the reference sorts all V logits to find the nucleus.  Here the boundary element
+// is found with an 8-pass, 4-bit radix select over order-preserving float keys (per-thread private bins, so no
+// shared-memory atomics), accumulating probability mass in double.  The kept set is identical to the
+// reference's "sort, cumsum, shift-right" rule: an element is kept iff the mass of the elements ranked
+// strictly before it is <= top_p (the first element crossing the threshold is kept, the top-1 always).
+#include <float.h>
+
+#include "common.cuh"
+#include "internal.h"
+
+namespace ccb {
+
+namespace {
+
+constexpr int kSampThreads = 1024;
+
+__device__ __forceinline__ uint32_t order_key(float x) {
+  const uint32_t u = __float_as_uint(x);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// Philox4x32-10 (Salmon et al.), the counter-based generator used when no explicit noise tensor is given.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+__device__ __forceinline__ float philox_exp1(unsigned long long seed, unsigned long long row, uint32_t step,
+                                             uint32_t v) {
+  const uint4 c = make_uint4(v >> 2, step, static_cast<uint32_t>(row), static_cast<uint32_t>(row >> 32));
+  const uint2 k = make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+  const uint4 r = philox4x32_10(c, k);
+  const uint32_t w = (v & 3) == 0 ? r.x : (v & 3) == 1 ? r.y : (v & 3) == 2 ? r.z : r.w;
+  const float u = (static_cast<float>(w >> 8) + 0.5f) * (1.0f / 16777216.0f);  // (0,1)
+  return -logf(u);
+}
+
+struct ArgMax {
+  float v;
+  int i;
+};
+__device__ __forceinline__ ArgMax argmax_better(ArgMax a, ArgMax b) {
+  // larger value wins; equal values -> lower index wins
+  if (b.v > a.v || (b.v == a.v && b.i < a.i)) return b;
+  return a;
+}
+__device__ __forceinline__ ArgMax block_argmax(ArgMax a, ArgMax* scratch /*>=32*/) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ArgMax b;
+    b.v = __shfl_xor_sync(0xffffffffu, a.v, o);
+    b.i = __shfl_xor_sync(0xffffffffu, a.i, o);
+    a = argmax_better(a, b);
+  }
+  __syncthreads();
+  if (lane == 0) scratch[w] = a;
+  __syncthreads();
+  ArgMax r;
+  r.v = -INFINITY;
+  r.i = 0x7fffffff;
+  if (lane < nw) r = scratch[lane];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ArgMax b;
+    b.v = __shfl_xor_sync(0xffffffffu, r.v, o);
+    b.i = __shfl_xor_sync(0xffffffffu, r.i, o);
+    r = argmax_better(r, b);
+  }
+  return r;
+}
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double block_sum_d(double v, double* scratch /*>=32*/) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum_d(v);
+  __syncthreads();
+  if (lane == 0) scratch[w] = v;
+  __syncthreads();
+  double r = (lane < nw) ? scratch[lane] : 0.0;
+  return warp_sum_d(r);
+}
+__device__ __forceinline__ int block_sum_i(int v, int* scratch) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if (lane == 0) scratch[w] = v;
+  __syncthreads();
+  int r = (lane < nw) ? scratch[lane] : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------------ greedy
+__global__ void __launch_bounds__(kSampThreads) greedy_kernel(const float* __restrict__ logits, long long ld, int V,
+                                                              int* __restrict__ next) {
+  __shared__ ArgMax scratch[32];
+  const float* row = logits + static_cast<long long>(blockIdx.x) * ld;
+  ArgMax a;
+  a.v = -INFINITY;
+  a.i = 0x7fffffff;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) {
+    ArgMax b;
+    b.v = row[v];
+    b.i = v;
+    a = argmax_better(a, b);
+  }
+  a = block_argmax(a, scratch);
+  if (threadIdx.x == 0) next[blockIdx.x] = a.i;
+}
+
+// ------------------------------------------------------------------------------------------------ top-k / top-p
+// 4-bit radix select over the order keys of vals[0..V).  mode 0: k-th largest (by count, 1-based `kth`).
+// mode 1: first element (descending) at which the cumulative probability mass exceeds top_p, where the mass of
+// element i is expf(vals[i] - vmax) * inv_sum.  Returns through shared scalars:
+//   sel_key  : key of the boundary element (0 when the target is never reached -> keep everything)
+//   mass_gt  : mode 1: mass strictly above the boundary key;   cnt_eq: elements equal to the boundary key
+struct SelectResult {
+  uint32_t key;
+  double mass_gt;
+  int cnt_eq;
+  int reached;
+};
+
+__device__ SelectResult radix_select(const float* vals, int V, int mode, int kth, float top_p, float vmax,
+                                     float inv_sum, double* dscratch /*32 + 16*/, int* iscratch /*32 + 16*/) {
+  uint32_t prefix = 0;
+  double mass_above = 0.0;
+  int cnt_above = 0;
+  int reached = 1;
+  int cnt_eq = 0;
+  double* bin_mass = dscratch + 32;
+  int* bin_cnt = iscratch + 32;
+  for (int nib = 7; nib >= 0; --nib) {
+    const int shift = nib * 4;
+    double m[16];
+    int c[16];
+#pragma unroll
+    for (int b = 0; b < 16; ++b) {
+      m[b] = 0.0;
+      c[b] = 0;
+    }
+    for (int v = threadIdx.x; v < V; v += blockDim.x) {
+      const float x = vals[v];
+      const uint32_t key = order_key(x);
+      const bool match = (nib == 7) || ((key >> (shift + 4)) == (prefix >> (shift + 4)));
+      if (match) {
+        const int b = (key >> shift) & 15;
+        double pm = 0.0;
+        if (mode == 1) pm = static_cast<double>(expf(x - vmax) * inv_sum);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          if (q == b) {
+            m[q] += pm;
+            c[q] += 1;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < 16; ++b) {
+      const int cb = block_sum_i(c[b], iscratch);
+      double mb = 0.0;
+      if (mode == 1) mb = block_sum_d(m[b], dscratch);
+      if (threadIdx.x == 0) {
+        bin_cnt[b] = cb;
+        bin_mass[b] = mb;
+      }
+    }
+    __syncthreads();
+    // every thread scans the 16 totals identically
+    int chosen = -1;
+    for (int b = 15; b >= 0; --b) {
+      if (bin_cnt[b] == 0) continue;
+      bool hit;
+      if (mode == 0)
+        hit = (cnt_above + bin_cnt[b] >= kth);
+      else
+        hit = (static_cast<float>(mass_above + bin_mass[b]) > top_p);
+      if (hit) {
+        chosen = b;
+        break;
+      }
+      cnt_above += bin_cnt[b];
+      mass_above += bin_mass[b];
+    }
+    if (chosen < 0) {
+      reached = 0;
+      break;
+    }
+    prefix |= static_cast<uint32_t>(chosen) << shift;
+    cnt_eq = bin_cnt[chosen];
+    __syncthreads();
+  }
+  __syncthreads();
+  SelectResult r;
+  r.key = reached ? prefix : 0u;
+  r.mass_gt = mass_above;
+  r.cnt_eq = cnt_eq;
+  r.reached = reached;
+  return r;
+}
+
+struct TopPArgs {
+  const float* logits;
+  long long ld;
+  int V;
+  float temperature;
+  float top_p;
+  int top_k;
+  const float* top_p_rows;
+  const int* top_k_rows;
+  float rep_pen;
+  const int* history;
+  long long ld_hist;
+  const int* hist_len;
+  int hist_len_scalar;
+  int hist_len_from_step;
+  const float* q_noise;
+  long long ldq;
+  long long q_step_stride;
+  unsigned long long seed;
+  const long long* row_ids;
+  const int* step;
+  int step_scalar;
+  float* filtered_out;
+  int* alt_out;
+  int* next;
+};
+
+__global__ void __launch_bounds__(kSampThreads) top_p_kernel(const TopPArgs a) {
+  extern __shared__ float vals[];  // V floats
+  __shared__ double dscratch[48];
+  __shared__ int iscratch[48];
+  __shared__ ArgMax ascratch[32];
+  __shared__ float fscratch[32];
+  const int b = blockIdx.x;
+  const int V = a.V;
+  const float* row = a.logits + static_cast<long long>(b) * a.ld;
+
+  for (int v = threadIdx.x; v < V; v += blockDim.x) vals[v] = row[v];
+  __syncthreads();
+  // repetition penalty (values computed from the ORIGINAL logits, like gather -> where -> scatter_)
+  if (a.rep_pen != 1.0f && a.history != nullptr) {
+    const int hl = a.hist_len ? a.hist_len[b] : (a.hist_len_from_step && a.step ? *a.step : a.hist_len_scalar);
+    for (int t = threadIdx.x; t < hl; t += blockDim.x) {
+      const int tok = a.history[static_cast<long long>(b) * a.ld_hist + t];
+      if (tok >= 0 && tok < V) {
+        const float x = row[tok];
+        vals[tok] = (x < 0.f) ? x * a.rep_pen : x / a.rep_pen;
+      }
+    }
+    __syncthreads();
+  }
+  const float T = a.temperature > 0.f ? a.temperature : 1.0f;
+  if (T != 1.0f) {
+    for (int v = threadIdx.x; v < V; v += blockDim.x) vals[v] = vals[v] / T;
+    __syncthreads();
+  }
+
+  // ---- top-k: remove everything strictly below the k-th largest value (ties at the cutoff survive)
+  int k = a.top_k_rows ? a.top_k_rows[b] : a.top_k;
+  if (k > V) k = V;
+  if (k > 0) {
+    const SelectResult r = radix_select(vals, V, 0, k, 0.f, 0.f, 0.f, dscratch, iscratch);
+    for (int v = threadIdx.x; v < V; v += blockDim.x)
+      if (order_key(vals[v]) < r.key) vals[v] = -INFINITY;
+    __syncthreads();
+  }
+
+  // ---- row max and softmax denominator of the (top-k filtered) row
+  float mx = -INFINITY;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) mx = fmaxf(mx, vals[v]);
+  mx = block_max(mx, fscratch);
+  float sum = 0.f;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) sum += expf(vals[v] - mx);
+  sum = block_sum(sum, fscratch);
+
+  // ---- top-p
+  const float top_p = a.top_p_rows ? a.top_p_rows[b] : a.top_p;
+  if (top_p > 0.f) {
+    const SelectResult r = radix_select(vals, V, 1, 0, top_p, mx, 1.0f / sum, dscratch, iscratch);
+    if (r.reached) {
+      // how many of the elements equal to the boundary key are kept (usually exactly one)
+      int keep_eq = r.cnt_eq;
+      if (r.cnt_eq > 1) {
+        // boundary probability: all ties share it
+        float xb = 0.f;
+        {
+          const uint32_t kk = r.key;
+          const uint32_t u = (kk & 0x80000000u) ? (kk & 0x7fffffffu) : ~kk;
+          xb = __uint_as_float(u);
+        }
+        const double pb = static_cast<double>(expf(xb - mx) * (1.0f / sum));
+        keep_eq = 1;
+        while (keep_eq < r.cnt_eq && !(static_cast<float>(r.mass_gt + keep_eq * pb) > top_p)) ++keep_eq;
+      }
+      if (keep_eq >= r.cnt_eq) {
+        for (int v = threadIdx.x; v < V; v += blockDim.x)
+          if (order_key(vals[v]) < r.key) vals[v] = -INFINITY;
+      } else {
+        // rare: keep only the first keep_eq ties in index order -> blocked ranges + block scan of tie counts
+        const int per = (V + blockDim.x - 1) / blockDim.x;
+        const int lo = threadIdx.x * per, hi = min(V, lo + per);
+        int mine = 0;
+        for (int v = lo; v < hi; ++v) mine += (order_key(vals[v]) == r.key);
+        __shared__ int tie_prefix[kSampThreads];
+        tie_prefix[threadIdx.x] = mine;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          int run = 0;
+          for (int t = 0; t < blockDim.x; ++t) {
+            const int c = tie_prefix[t];
+            tie_prefix[t] = run;
+            run += c;
+          }
+        }
+        __syncthreads();
+        int rank = tie_prefix[threadIdx.x];
+        for (int v = lo; v < hi; ++v) {
+          const uint32_t key = order_key(vals[v]);
+          if (key < r.key) {
+            vals[v] = -INFINITY;
+          } else if (key == r.key) {
+            if (rank >= keep_eq) vals[v] = -INFINITY;
+            ++rank;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (a.filtered_out) {
+    float* fo = a.filtered_out + static_cast<long long>(b) * a.ld;
+    for (int v = threadIdx.x; v < V; v += blockDim.x) fo[v] = vals[v];
+  }
+
+  // ---- softmax over the kept set and multinomial == argmax(p / q), q ~ Exp(1)
+  float ksum = 0.f;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) ksum += expf(vals[v] - mx);
+  ksum = block_sum(ksum, fscratch);
+  const unsigned long long rid = a.row_ids ? static_cast<unsigned long long>(a.row_ids[b]) : static_cast<unsigned long long>(b);
+  const uint32_t step = a.step ? static_cast<uint32_t>(*a.step) : static_cast<uint32_t>(a.step_scalar);
+  const float* qrow = a.q_noise ? a.q_noise + static_cast<long long>(step) * a.q_step_stride + static_cast<long long>(b) * a.ldq : nullptr;
+  ArgMax best;
+  best.v = -INFINITY;
+  best.i = 0x7fffffff;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) {
+    const float x = vals[v];
+    if (x == -INFINITY) continue;
+    const float p = expf(x - mx) / ksum;
+    const float q = qrow ? qrow[v] : philox_exp1(a.seed, rid, step, v);
+    ArgMax c;
+    c.v = p / q;
+    c.i = v;
+    best = argmax_better(best, c);
+  }
+  const ArgMax win = block_argmax(best, ascratch);
+  if (threadIdx.x == 0) a.next[b] = win.i;
+  if (a.alt_out) {
+    // second draw without replacement: best ratio excluding the winner
+    ArgMax second;
+    second.v = -INFINITY;
+    second.i = 0x7fffffff;
+    for (int v = threadIdx.x; v < V; v += blockDim.x) {
+      const float x = vals[v];
+      if (x == -INFINITY || v == win.i) continue;
+      const float p = expf(x - mx) / ksum;
+      const float q = qrow ? qrow[v] : philox_exp1(a.seed, rid, step, v);
+      ArgMax c;
+      c.v = p / q;
+      c.i = v;
+      second = argmax_better(second, c);
+    }
+    const ArgMax w2 = block_argmax(second, ascratch);
+    if (threadIdx.x == 0) a.alt_out[b] = (w2.i == 0x7fffffff) ? win.i : w2.i;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ beam step
+// One CTA per image.  Follows inference.py:98-131:
+//   lp = log(softmax(logits / T));  first step: scores, tokens = top-beam(lp[row 0])
+//   later: stopped rows contribute only token 0 with lp 0; sum = score + lp; len += !stopped; avg = sum / len;
+//          flat top-beam over beam*V of avg (ties: lowest flat index); src = idx / V; tok = idx % V;
+//          len = len[src]; score = avg * len; stopped = stopped[src] | (tok == stop)
+// Also permutes the per-row token history and block tables so the next decode step reads the right KV.
+constexpr int kMaxBeam = 8;
+
+struct BeamArgs {
+  const float* logits;      // step 0: [N, ld] (one row per image); later: [N*beam, ld]
+  long long ld;
+  int beam, V;
+  float temperature;
+  int stop_token;
+  float* scores;
+  float* seq_lengths;
+  uint8_t* has_stopped;
+  int* tokens;              // [N, beam, max_len]
+  int max_len;
+  const int* step;
+  int* next_tokens;         // [N*beam]
+  int* src_rows;            // [N*beam]
+  int* block_table;         // [N*beam, max_pages] permuted in place (may be null)
+  int max_pages;
+  const int* ctx_len;       // [N*beam] tokens currently cached per row (entries < ctx are permuted)
+};
+
+struct Cand {
+  float v;
+  int idx;  // flat index r * V + tok
+};
+__device__ __forceinline__ bool cand_better(const Cand& a, const Cand& b) {  // a ranks before b
+  return a.v > b.v || (a.v == b.v && a.idx < b.idx);
+}
+
+__global__ void __launch_bounds__(kSampThreads) beam_step_kernel(const BeamArgs a) {
+  __shared__ float fscratch[32];
+  __shared__ float row_max[kMaxBeam], row_lse_sum[kMaxBeam];
+  __shared__ Cand wcand[32 * kMaxBeam];
+  __shared__ Cand top[kMaxBeam];
+  __shared__ float s_scores[kMaxBeam], s_len[kMaxBeam];
+  __shared__ uint8_t s_stop[kMaxBeam];
+  extern __shared__ int perm_buf[];  // beam * max(max_len, max_pages) ints
+  const int n = blockIdx.x;
+  const int beam = a.beam, V = a.V;
+  const int step = *a.step;
+  const bool first = (step == 0);
+  const int rows = first ? 1 : beam;
+  const float T = a.temperature > 0.f ? a.temperature : 1.0f;
+
+  if (threadIdx.x < beam) {
+    s_scores[threadIdx.x] = first ? 0.f : a.scores[n * beam + threadIdx.x];
+    s_len[threadIdx.x] = first ? 1.f : a.seq_lengths[n * beam + threadIdx.x];
+    s_stop[threadIdx.x] = first ? 0 : a.has_stopped[n * beam + threadIdx.x];
+  }
+  __syncthreads();
+  // seq_lengths[~has_stopped] += 1  (not on the first step)
+  if (!first && threadIdx.x < beam && !s_stop[threadIdx.x]) s_len[threadIdx.x] += 1.f;
+
+  // per-row softmax statistics
+  for (int r = 0; r < rows; ++r) {
+    const float* row = a.logits + (first ? static_cast<long long>(n) : static_cast<long long>(n) * beam + r) * a.ld;
+    float mx = -INFINITY;
+    for (int v = threadIdx.x; v < V; v += blockDim.x) mx = fmaxf(mx, row[v] / T);
+    mx = block_max(mx, fscratch);
+    float sm = 0.f;
+    for (int v = threadIdx.x; v < V; v += blockDim.x) sm += expf(row[v] / T - mx);
+    sm = block_sum(sm, fscratch);
+    if (threadIdx.x == 0) {
+      row_max[r] = mx;
+      row_lse_sum[r] = sm;
+    }
+  }
+  __syncthreads();
+
+  // thread-local top-kMaxBeam candidates (fixed size keeps them in registers; top-beam is a subset)
+  Cand loc[kMaxBeam];
+#pragma unroll
+  for (int q = 0; q < kMaxBeam; ++q) {
+    loc[q].v = -INFINITY;
+    loc[q].idx = 0x7fffffff;
+  }
+  auto push = [&](float val, int idx) {
+    Cand c;
+    c.v = val;
+    c.idx = idx;
+    if (!cand_better(c, loc[kMaxBeam - 1])) return;
+    loc[kMaxBeam - 1] = c;
+#pragma unroll
+    for (int q = kMaxBeam - 1; q > 0; --q) {
+      if (cand_better(loc[q], loc[q - 1])) {
+        const Cand t = loc[q];
+        loc[q] = loc[q - 1];
+        loc[q - 1] = t;
+      }
+    }
+  };
+  for (int r = 0; r < rows; ++r) {
+    const float* row = a.logits + (first ? static_cast<long long>(n) : static_cast<long long>(n) * beam + r) * a.ld;
+    if (!first && s_stop[r]) {
+      // logits[has_stopped] = -inf; logits[has_stopped, 0] = 0  -> only token 0 is a finite candidate
+      if (threadIdx.x == 0) push((s_scores[r] + 0.f) / s_len[r], r * V);
+      continue;
+    }
+    const float mx = row_max[r], sm = row_lse_sum[r];
+    for (int v = threadIdx.x; v < V; v += blockDim.x) {
+      const float lp = logf(expf(row[v] / T - mx) / sm);  // softmax(-1).log()
+      const float val = first ? lp : (s_scores[r] + lp) / s_len[r];
+      push(val, r * V + v);
+    }
+  }
+  // warp merge: repeatedly extract the best head among the 32 lanes
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  {
+    int head = 0;
+    for (int k = 0; k < beam; ++k) {
+      Cand mine;
+      mine.v = -INFINITY;
+      mine.idx = 0x7fffffff;
+#pragma unroll
+      for (int q = 0; q < kMaxBeam; ++q)
+        if (q == head) mine = loc[q];
+      if (head >= kMaxBeam) {
+        mine.v = -INFINITY;
+        mine.idx = 0x7fffffff;
+      }
+      Cand best = mine;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        Cand oth;
+        oth.v = __shfl_xor_sync(0xffffffffu, best.v, o);
+        oth.idx = __shfl_xor_sync(0xffffffffu, best.idx, o);
+        if (cand_better(oth, best)) best = oth;
+      }
+      if (best.idx == mine.idx && best.idx != 0x7fffffff) ++head;
+      if (lane == 0) wcand[w * kMaxBeam + k] = best;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // final merge of 32 sorted lists by one thread (32 * beam candidates)
+    int heads[32];
+    for (int q = 0; q < 32; ++q) heads[q] = 0;
+    const int nw = blockDim.x >> 5;
+    for (int k = 0; k < beam; ++k) {
+      int bw = -1;
+      Cand best;
+      best.v = -INFINITY;
+      best.idx = 0x7fffffff;
+      for (int q = 0; q < nw; ++q) {
+        if (heads[q] >= beam) continue;
+        const Cand c = wcand[q * kMaxBeam + heads[q]];
+        if (bw < 0 || cand_better(c, best)) {
+          best = c;
+          bw = q;
+        }
+      }
+      heads[bw]++;
+      top[k] = best;
+    }
+  }
+  __syncthreads();
+
+  // bookkeeping
+  __shared__ int s_src[kMaxBeam], s_tok[kMaxBeam];
+  if (threadIdx.x < beam) {
+    const int k = threadIdx.x;
+    const Cand c = top[k];
+    int src, tok;
+    float new_len, new_score;
+    uint8_t stopped;
+    if (first) {
+      src = 0;
+      tok = c.idx;
+      new_len = 1.f;
+      new_score = c.v;
+      stopped = 0;
+    } else {
+      src = c.idx / V;
+      tok = c.idx % V;
+      new_len = s_len[src];
+      new_score = c.v * new_len;
+      stopped = s_stop[src];
+    }
+    stopped = stopped | (tok == a.stop_token ? 1 : 0);
+    s_src[k] = src;
+    s_tok[k] = tok;
+    a.scores[n * beam + k] = new_score;
+    a.seq_lengths[n * beam + k] = new_len;
+    a.has_stopped[n * beam + k] = stopped;
+    a.next_tokens[n * beam + k] = tok;
+    a.src_rows[n * beam + k] = n * beam + src;
+  }
+  __syncthreads();
+  // tokens = cat(tokens[src], tok)
+  {
+    int* tk = a.tokens + static_cast<long long>(n) * beam * a.max_len;
+    if (!first) {
+      for (int idx = threadIdx.x; idx < beam * step; idx += blockDim.x) perm_buf[idx] = tk[(idx / step) * a.max_len + idx % step];
+      __syncthreads();
+      for (int idx = threadIdx.x; idx < beam * step; idx += blockDim.x) {
+        const int k = idx / step, t = idx % step;
+        tk[k * a.max_len + t] = perm_buf[s_src[k] * step + t];
+      }
+    }
+    if (threadIdx.x < beam && step < a.max_len) tk[threadIdx.x * a.max_len + step] = s_tok[threadIdx.x];
+  }
+  // block tables: row k inherits the cached-token entries of its source row
+  if (!first && a.block_table != nullptr) {
+    __syncthreads();
+    const int ctx = a.ctx_len[n * beam];
+    int* bt = a.block_table + static_cast<long long>(n) * beam * a.max_pages;
+    for (int idx = threadIdx.x; idx < beam * ctx; idx += blockDim.x) perm_buf[idx] = bt[(idx / ctx) * a.max_pages + idx % ctx];
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < beam * ctx; idx += blockDim.x) {
+      const int k = idx / ctx, t = idx % ctx;
+      bt[k * a.max_pages + t] = perm_buf[s_src[k] * ctx + t];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ bookkeeping
+__global__ void advance_kernel(const int* __restrict__ next, int rows, int* tokens_out, int max_len, int* lengths,
+                               int* stops, uint8_t* finished, int* ctx_len, int* step, int stop_token, int max_stops,
+                               int eos_token) {
+  const int st = *step;
+  for (int r = threadIdx.x; r < rows; r += blockDim.x) {
+    const int tok = next[r];
+    if (tokens_out && st < max_len) tokens_out[static_cast<long long>(r) * max_len + st] = tok;
+    if (finished && !finished[r]) {
+      int sc = stops[r];
+      if (tok == stop_token) sc += 1;
+      stops[r] = sc;
+      const bool fin = (max_stops > 0 && sc >= max_stops) || (eos_token >= 0 && tok == eos_token);
+      lengths[r] = st + 1;
+      if (fin) finished[r] = 1;
+    }
+    if (ctx_len) ctx_len[r] += 1;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *step = st + 1;
+}
+
+}  // namespace
+
+int sample_greedy(const float* logits, long long ld, int B, int V, int* next, cudaStream_t s) {
+  if (B <= 0) return 0;
+  greedy_kernel<<<B, kSampThreads, 0, s>>>(logits, ld, V, next);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
+int sample_top_p(const float* logits, long long ld, int B, int V, const SampleParams& sp, int* next,
+                 cudaStream_t s) {
+  if (B <= 0) return 0;
+  const size_t smem = static_cast<size_t>(V) * sizeof(float);
+  if (smem > 208 * 1024) return (int)cudaErrorInvalidValue;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(top_p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  TopPArgs a;
+  a.logits = logits; a.ld = ld; a.V = V;
+  a.temperature = sp.temperature; a.top_p = sp.top_p; a.top_k = sp.top_k;
+  a.top_p_rows = sp.top_p_rows; a.top_k_rows = sp.top_k_rows;
+  a.rep_pen = sp.repetition_penalty; a.history = sp.history; a.ld_hist = sp.ld_hist;
+  a.hist_len = sp.hist_len; a.hist_len_scalar = sp.hist_len_scalar; a.hist_len_from_step = sp.hist_len_from_step;
+  a.q_noise = sp.q_noise; a.ldq = sp.ldq; a.q_step_stride = sp.q_step_stride; a.seed = sp.seed; a.row_ids = sp.row_ids;
+  a.step = sp.step; a.step_scalar = sp.step_scalar;
+  a.filtered_out = sp.filtered_out; a.alt_out = sp.alt_out; a.next = next;
+  top_p_kernel<<<B, kSampThreads, smem, s>>>(a);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
+int beam_step(const float* logits, long long ld, int N, int beam, int V, float temperature, int stop_token,
+              const BeamState& st, int* next_tokens, int* src_rows, int* block_table, int max_pages,
+              const int* ctx_len, cudaStream_t s) {
+  if (N <= 0) return 0;
+  if (beam < 1 || beam > kMaxBeam) return (int)cudaErrorInvalidValue;
+  BeamArgs a;
+  a.logits = logits; a.ld = ld; a.beam = beam; a.V = V; a.temperature = temperature; a.stop_token = stop_token;
+  a.scores = st.scores; a.seq_lengths = st.seq_lengths; a.has_stopped = st.has_stopped; a.tokens = st.tokens;
+  a.max_len = st.max_len; a.step = st.step; a.next_tokens = next_tokens; a.src_rows = src_rows;
+  a.block_table = block_table; a.max_pages = max_pages; a.ctx_len = ctx_len;
+  const int m = st.max_len > max_pages ? st.max_len : max_pages;
+  const size_t smem = static_cast<size_t>(beam) * m * sizeof(int);
+  if (smem > 64 * 1024) return (int)cudaErrorInvalidValue;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(beam_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  beam_step_kernel<<<N, kSampThreads, smem, s>>>(a);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
+__global__ void increment_kernel(int* x, int rows, int* scalar) {
+  for (int r = threadIdx.x; r < rows; r += blockDim.x) x[r] += 1;
+  if (scalar && threadIdx.x == 0) *scalar += 1;
+}
+}  // namespace ccb
+namespace ccb {
+int increment_rows(int* x, int rows, int* scalar, cudaStream_t s) {
+  increment_kernel<<<1, 1024, 0, s>>>(x, rows, scalar);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
+int advance_rows(const int* next, int rows, int* tokens_out, int max_len, int* lengths, int* stops, uint8_t* finished,
+                 int* ctx_len, int* step, int stop_token, int max_stops, int eos_token, cudaStream_t s) {
+  advance_kernel<<<1, 1024, 0, s>>>(next, rows, tokens_out, max_len, lengths, stops, finished, ctx_len, step,
+                                    stop_token, max_stops, eos_token);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
+}  // namespace ccb

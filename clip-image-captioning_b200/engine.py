@@ -1,0 +1,339 @@
+"""Python host side of libclipcap_b200: one `Engine` per GPU wraps a ccb_ctx.
+
+PyTorch is used for device memory and streams only; every computation is a call through the C ABI
+(include/clipcap_b200.h).  All tensors handed to the library are CUDA tensors on the engine's device.
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib
+from ._lib import GenParams, ModelDesc
+
+
+@dataclass
+class EngineConfig:
+    """Shapes of the three networks on the path and the capacities of one context.
+
+    Defaults are BASELINE.json config 2: ViT-B/32 + 8-layer Transformer mapper (prefix 40, clip_length 40) +
+    GPT2-XL.  `lm_*` follow HF GPT2Config / GPTJConfig; `map_*` follow CLIPCaptionModel hparams
+    (reference model.py:53-78); `vit_*` follow OpenAI CLIP ViT-B/32.
+    """
+    lm_arch: str = "gpt2"            # "gpt2" | "gptj"
+    lm_d: int = 1600
+    lm_layers: int = 48
+    lm_heads: int = 25
+    lm_vocab: int = 50257
+    lm_n_pos: int = 1024
+    lm_rotary_dim: int = 0
+    lm_ln_eps: float = 1e-5
+    map_kind: str = "transformer"    # "transformer" | "mlp" | "none"
+    map_dim_clip: int = 512          # hparams.prefix_size
+    map_clip_len: int = 40           # hparams.clip_prefix_length
+    map_prefix_len: int = 40         # hparams.prefix_length
+    map_heads: int = 8
+    map_layers: int = 8
+    map_mlp_ratio: float = 4.0
+    map_hidden: int = 0              # 0 -> int(lm_d * mlp_ratio) (transformer) / lm_d * prefix_len // 2 (mlp)
+    map_act: str = "relu"
+    vit: bool = True
+    vit_image: int = 224
+    vit_patch: int = 32
+    vit_width: int = 768
+    vit_layers: int = 12
+    vit_heads: int = 12
+    vit_out: int = 512
+    max_images: int = 64
+    max_beam: int = 1
+    max_ctx: int = 80
+    max_lm_tokens: int = 0           # 0 -> max_images * max_ctx
+    page_tokens: int = 16
+
+    def desc(self) -> ModelDesc:
+        d = ModelDesc()
+        d.lm_arch = {"gpt2": _lib.LM_GPT2, "gptj": _lib.LM_GPTJ}[self.lm_arch]
+        d.lm_d, d.lm_layers, d.lm_heads, d.lm_vocab = self.lm_d, self.lm_layers, self.lm_heads, self.lm_vocab
+        d.lm_n_pos, d.lm_rotary_dim, d.lm_ln_eps = self.lm_n_pos, self.lm_rotary_dim, self.lm_ln_eps
+        d.map_kind = {"none": _lib.MAP_NONE, "transformer": _lib.MAP_TRANSFORMER, "mlp": _lib.MAP_MLP}[self.map_kind]
+        d.map_dim_clip, d.map_clip_len, d.map_prefix_len = self.map_dim_clip, self.map_clip_len, self.map_prefix_len
+        d.map_heads, d.map_layers = self.map_heads, self.map_layers
+        hidden = self.map_hidden
+        if hidden == 0:
+            hidden = (self.lm_d * self.map_prefix_len) // 2 if self.map_kind == "mlp" else int(self.lm_d * self.map_mlp_ratio)
+        d.map_hidden = hidden
+        d.map_act = _lib.ACT[self.map_act]
+        d.vit_present = 1 if self.vit else 0
+        d.vit_image, d.vit_patch, d.vit_width = self.vit_image, self.vit_patch, self.vit_width
+        d.vit_layers, d.vit_heads, d.vit_out = self.vit_layers, self.vit_heads, self.vit_out
+        d.max_images, d.max_beam, d.max_ctx = self.max_images, self.max_beam, self.max_ctx
+        d.max_lm_tokens = self.max_lm_tokens or self.max_images * self.max_ctx
+        d.page_tokens = self.page_tokens
+        return d
+
+
+_TORCH_DTYPE = {torch.float32: _lib.DTYPE_F32, torch.float16: _lib.DTYPE_F16, torch.bfloat16: _lib.DTYPE_BF16}
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class Engine:
+    """A ccb_ctx bound to one CUDA device."""
+
+    def __init__(self, cfg: EngineConfig, device: int = 0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("clipcap_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.cfg = cfg
+        self.device = torch.device("cuda", device)
+        torch.cuda.init()
+        with torch.cuda.device(self.device):
+            torch.zeros(1, device=self.device)  # make sure the primary context exists
+            h = C.c_void_p()
+            desc = cfg.desc()
+            if self.lib.ccb_create(C.byref(h), C.byref(desc), device) != 0:
+                raise RuntimeError(self.lib.ccb_last_error(None).decode())
+        self._h = h
+        self._desc = desc
+        self.ldv = (cfg.lm_vocab + 63) // 64 * 64
+        self._keep = []  # tensors referenced by in-flight asynchronous calls
+
+    # ------------------------------------------------------------------------------------------ plumbing
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.ccb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _check(self, status: int):
+        if status != 0:
+            raise RuntimeError(self.lib.ccb_last_error(self._h).decode())
+
+    def _dev(self, t: torch.Tensor, dtype=None) -> torch.Tensor:
+        t = t.to(self.device, dtype=dtype) if dtype is not None else t.to(self.device)
+        return t.contiguous()
+
+    @property
+    def device_bytes(self) -> int:
+        return int(self.lib.ccb_device_bytes(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.ccb_launch_count(self._h))
+
+    def last_timing(self):
+        """(prefill_ms, decode_ms, decode_steps) of the last generate call; synchronises the device."""
+        torch.cuda.synchronize(self.device)
+        a, b, n = C.c_float(), C.c_float(), C.c_int()
+        self._check(self.lib.ccb_last_timing(self._h, C.byref(a), C.byref(b), C.byref(n)))
+        return a.value, b.value, n.value
+
+    # ------------------------------------------------------------------------------------------ weights
+    def load_state_dict(self, sd: Dict[str, torch.Tensor], prefix: str = "", strict: bool = True):
+        """Ingest tensors named as in the reference checkpoint (`language_model.*`, `clip_project.*`,
+        `visual_encoder.*` / `visual.*`); `prefix` is prepended to every key (e.g. "clip_project." for a bare
+        TransformerMapper.state_dict()).  Returns the list of keys the context did not use."""
+        unused = []
+        with torch.cuda.device(self.device):
+            for k, v in sd.items():
+                if not torch.is_tensor(v) or v.dtype not in _TORCH_DTYPE:
+                    unused.append(k)
+                    continue
+                t = self._dev(v.detach())
+                shape = (C.c_int64 * max(t.dim(), 1))(*(t.shape if t.dim() else (1,)))
+                r = self.lib.ccb_load_weight(self._h, (prefix + k).encode(), _ptr(t), _TORCH_DTYPE[t.dtype], shape,
+                                             max(t.dim(), 1), self._stream())
+                if r < 0:
+                    self._check(r)
+                if r == 1:
+                    unused.append(k)
+            torch.cuda.synchronize(self.device)
+        return unused
+
+    def weights_complete(self) -> bool:
+        return self.lib.ccb_weights_complete(self._h) == 0
+
+    def check_weights(self):
+        self._check(self.lib.ccb_weights_complete(self._h))
+
+    # ------------------------------------------------------------------------------------------ stages
+    def vit_encode(self, images: torch.Tensor) -> torch.Tensor:
+        images = self._dev(images)
+        if images.dtype not in _TORCH_DTYPE:
+            images = images.float()
+        B = images.shape[0]
+        out = torch.empty(B, self.cfg.vit_out, device=self.device, dtype=torch.float32)
+        self._check(self.lib.ccb_vit_encode(self._h, _ptr(images), _TORCH_DTYPE[images.dtype], B, _ptr(out), self._stream()))
+        return out
+
+    def map_prefix(self, feat: torch.Tensor) -> torch.Tensor:
+        feat = self._dev(feat, torch.float32)
+        B = feat.shape[0]
+        out = torch.empty(B, self.cfg.map_prefix_len, self.cfg.lm_d, device=self.device, dtype=torch.float32)
+        self._check(self.lib.ccb_map_prefix(self._h, _ptr(feat), B, _ptr(out), self._stream()))
+        return out
+
+    def embed_tokens(self, tokens: torch.Tensor) -> torch.Tensor:
+        tk = self._dev(tokens, torch.int32)
+        out = torch.empty(*tk.shape, self.cfg.lm_d, device=self.device, dtype=torch.float32)
+        if tk.numel():
+            self._check(self.lib.ccb_embed_tokens(self._h, _ptr(tk), tk.numel(), _ptr(out), self._stream()))
+        return out
+
+    def lm_forward(self, embeds: torch.Tensor, attention_mask: Optional[torch.Tensor] = None,
+                   last_only: bool = False) -> torch.Tensor:
+        embeds = self._dev(embeds, torch.float32)
+        B, S, _ = embeds.shape
+        mask = None
+        if attention_mask is not None:
+            mask = self._dev(attention_mask.to(torch.bool)).to(torch.uint8).contiguous()
+        rows = B if last_only else B * S
+        buf = torch.empty(rows, self.ldv, device=self.device, dtype=torch.float32)
+        self._check(self.lib.ccb_lm_forward(self._h, _ptr(embeds), B, S, _ptr(mask), _ptr(buf), self.ldv,
+                                            1 if last_only else 0, self._stream()))
+        V = self.cfg.lm_vocab
+        return buf[:, :V] if last_only else buf.view(B, S, self.ldv)[:, :, :V]
+
+    # ------------------------------------------------------------------------------------------ generation
+    def gen_params(self, mode: str, max_new_tokens: int, stop_token: int = 13, max_stops: int = 1, eos_token: int = -1,
+                   temperature: float = 1.0, top_p: float = 0.0, top_k: int = 0, repetition_penalty: float = 1.0,
+                   beam_size: int = 1, seed: int = 0, q_noise: Optional[torch.Tensor] = None,
+                   row_ids: Optional[torch.Tensor] = None, top_p_rows: Optional[torch.Tensor] = None,
+                   top_k_rows: Optional[torch.Tensor] = None):
+        p = GenParams()
+        p.mode = {"greedy": _lib.GEN_GREEDY, "sample": _lib.GEN_SAMPLE, "beam": _lib.GEN_BEAM}[mode]
+        p.max_new_tokens, p.stop_token, p.max_stops, p.eos_token = max_new_tokens, stop_token, max_stops, eos_token
+        p.temperature, p.top_p, p.top_k, p.repetition_penalty = temperature, top_p, top_k, repetition_penalty
+        p.beam_size, p.seed = beam_size, seed
+        keep = []
+        if q_noise is not None:
+            q_noise = self._dev(q_noise, torch.float32)
+            p.q_noise, p.q_ld = q_noise.data_ptr(), q_noise.shape[-1]
+            keep.append(q_noise)
+        if row_ids is not None:
+            row_ids = self._dev(row_ids, torch.int64)
+            p.row_ids = row_ids.data_ptr()
+            keep.append(row_ids)
+        if top_p_rows is not None:
+            top_p_rows = self._dev(top_p_rows, torch.float32)
+            p.top_p_rows = top_p_rows.data_ptr()
+            keep.append(top_p_rows)
+        if top_k_rows is not None:
+            top_k_rows = self._dev(top_k_rows, torch.int32)
+            p.top_k_rows = top_k_rows.data_ptr()
+            keep.append(top_k_rows)
+        p._keep = keep
+        return p
+
+    def _gen_outputs(self, p: GenParams, N: int):
+        T = p.max_new_tokens
+        if p.mode == _lib.GEN_BEAM:
+            tokens = torch.empty(N, p.beam_size, T, device=self.device, dtype=torch.int32)
+            lengths = torch.empty(N, p.beam_size, device=self.device, dtype=torch.int32)
+            scores = torch.empty(N, p.beam_size, device=self.device, dtype=torch.float32)
+        else:
+            tokens = torch.empty(N, T, device=self.device, dtype=torch.int32)
+            lengths = torch.empty(N, device=self.device, dtype=torch.int32)
+            scores = None
+        return tokens, lengths, scores
+
+    def generate(self, embeds: torch.Tensor, p: GenParams):
+        """Prefix embeddings [N, S0, d] -> (tokens, lengths, scores) on the device, whole loop on the GPU."""
+        embeds = self._dev(embeds, torch.float32)
+        N, S0, _ = embeds.shape
+        tokens, lengths, scores = self._gen_outputs(p, N)
+        self._check(self.lib.ccb_generate(self._h, C.byref(p), _ptr(embeds), N, S0, _ptr(tokens), _ptr(lengths),
+                                          _ptr(scores), self._stream()))
+        self._keep = [embeds, p]
+        return tokens, lengths, scores
+
+    def caption_images(self, images: torch.Tensor, p: GenParams, append_bos: int = -1):
+        """Images [N,3,H,W] -> (tokens, lengths, scores): ViT + mapper + generation in one library call."""
+        images = self._dev(images)
+        if images.dtype not in _TORCH_DTYPE:
+            images = images.float()
+        N = images.shape[0]
+        tokens, lengths, scores = self._gen_outputs(p, N)
+        self._check(self.lib.ccb_caption_images(self._h, C.byref(p), _ptr(images), _TORCH_DTYPE[images.dtype], N,
+                                                append_bos, _ptr(tokens), _ptr(lengths), _ptr(scores), self._stream()))
+        self._keep = [images, p]
+        return tokens, lengths, scores
+
+    # ------------------------------------------------------------------------------------------ samplers
+    def sample(self, logits: torch.Tensor, p: GenParams, history: Optional[torch.Tensor] = None, step: int = 0,
+               return_filtered: bool = False, return_alt: bool = False):
+        logits = self._dev(logits, torch.float32)
+        B, V = logits.shape
+        hist = self._dev(history, torch.int32) if history is not None and history.numel() else None
+        filt = torch.empty_like(logits) if return_filtered else None
+        nxt = torch.empty(B, device=self.device, dtype=torch.int32)
+        alt = torch.empty(B, device=self.device, dtype=torch.int32) if return_alt else None
+        self._check(self.lib.ccb_sample(self._h, _ptr(logits), logits.stride(0), B, V, C.byref(p), _ptr(hist),
+                                        hist.stride(0) if hist is not None else 0,
+                                        hist.shape[1] if hist is not None else 0, step, _ptr(filt), _ptr(nxt), _ptr(alt),
+                                        self._stream()))
+        return nxt, filt, alt
+
+    def argmax(self, logits: torch.Tensor) -> torch.Tensor:
+        logits = self._dev(logits, torch.float32)
+        B, V = logits.shape
+        nxt = torch.empty(B, device=self.device, dtype=torch.int32)
+        self._check(self.lib.ccb_argmax(self._h, _ptr(logits), logits.stride(0), B, V, _ptr(nxt), self._stream()))
+        return nxt
+
+    def beam_step(self, logits, scores, seq_lengths, has_stopped, tokens, step: int, beam: int, temperature=1.0,
+                  stop_token=13):
+        """One step of inference.py:98-131 for N images; state tensors are updated in place."""
+        logits = self._dev(logits, torch.float32)
+        N = scores.shape[0]
+        V = logits.shape[1]
+        nxt = torch.empty(N * beam, device=self.device, dtype=torch.int32)
+        src = torch.empty(N * beam, device=self.device, dtype=torch.int32)
+        self._check(self.lib.ccb_beam_step(self._h, _ptr(logits), logits.stride(0), N, beam, V, temperature, stop_token,
+                                           step, _ptr(scores), _ptr(seq_lengths), _ptr(has_stopped), _ptr(tokens),
+                                           tokens.shape[-1], _ptr(nxt), _ptr(src), self._stream()))
+        return nxt, src
+
+    # ------------------------------------------------------------------------------------------ single ops
+    def op_linear(self, x, w, bias=None, act="none", residual=None, out_dtype=torch.float32, orientation=0, bn=0,
+                  split_k=0):
+        """act(x @ w.T + bias) + residual with x [tokens, K] bf16, w [features, K] bf16 (tcgen05 GEMM)."""
+        x = self._dev(x, torch.bfloat16)
+        w = self._dev(w, torch.bfloat16)
+        tokens, K = x.shape
+        features = w.shape[0]
+        bias = self._dev(bias, torch.float32) if bias is not None else None
+        residual = self._dev(residual, torch.float32) if residual is not None else None
+        out = torch.empty(tokens, features, device=self.device, dtype=out_dtype)
+        self._check(self.lib.ccb_op_linear(self._h, _ptr(x), x.stride(0), tokens, _ptr(w), features, K, _ptr(bias),
+                                           _lib.ACT[act], _ptr(residual), residual.stride(0) if residual is not None else 0,
+                                           _ptr(out), out.stride(0), 1 if out_dtype == torch.bfloat16 else 0, orientation,
+                                           bn, split_k, self._stream()))
+        return out
+
+    def op_layernorm(self, x, gamma, beta, eps=1e-5):
+        x = self._dev(x, torch.float32)
+        rows, d = x.shape
+        y = torch.empty(rows, d, device=self.device, dtype=torch.bfloat16)
+        g, b = self._dev(gamma, torch.float32), self._dev(beta, torch.float32)  # keep both alive across the call
+        self._check(self.lib.ccb_op_layernorm(self._h, _ptr(x), _ptr(g), _ptr(b), eps, _ptr(y), rows, d, self._stream()))
+        return y
+
+    def op_attention(self, qkv, B, S, H, hd, causal=False, rotary_dim=0, scale=None):
+        qkv = self._dev(qkv, torch.bfloat16)
+        out = torch.empty(B * S, H * hd, device=self.device, dtype=torch.bfloat16)
+        self._check(self.lib.ccb_op_attention(self._h, _ptr(qkv), _ptr(out), B, S, H, hd,
+                                              scale if scale is not None else hd ** -0.5, 1 if causal else 0, rotary_dim,
+                                              self._stream()))
+        return out

@@ -1,0 +1,163 @@
+/* libclipcap_b200 -- C ABI of the B200-native caption-generation hot path.
+ *
+ * The reference (andreaskoepf/CLIP-Image-Captioning) is pure Python and has no FFI: its boundary for this path
+ * is the Python attribute surface listed in SURVEY.md section 8(b).  Each entry point below names the reference
+ * call it replaces (file:line in the reference tree); the Python host code in clip-image-captioning_b200/
+ * keeps the reference names/signatures and forwards to these functions through ctypes.
+ *
+ * Conventions
+ *   - return value 0 = OK, negative = error; ccb_last_error(ctx) (or ccb_last_error(NULL) for ccb_create
+ *     failures) returns a human-readable message.  No C++ exception crosses the ABI.
+ *   - every data pointer is a DEVICE pointer to a contiguous row-major tensor owned by the caller (PyTorch);
+ *     the library never frees caller memory and allocates only inside ccb_create.
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*); no host synchronisation except
+ *     where stated.  A ccb_ctx is bound to one device and is not thread-safe (one ctx per rank / GPU).
+ *   - there is no CPU fallback: without an sm_100 device ccb_create fails.
+ */
+#ifndef CLIPCAP_B200_H_
+#define CLIPCAP_B200_H_
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define CCB_API __attribute__((visibility("default")))
+#else
+#define CCB_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ccb_ctx ccb_ctx;
+
+enum { CCB_DTYPE_F32 = 0, CCB_DTYPE_F16 = 1, CCB_DTYPE_BF16 = 2 };
+enum { CCB_LM_GPT2 = 0, CCB_LM_GPTJ = 1 };
+enum { CCB_MAP_NONE = 0, CCB_MAP_TRANSFORMER = 1, CCB_MAP_MLP = 2 };
+/* activation codes (mapper act_fn_name, layers/Transformer.py:117-130; ViT QuickGELU; GPT gelu_new) */
+enum {
+  CCB_ACT_NONE = 0, CCB_ACT_RELU = 1, CCB_ACT_QUICKGELU = 2, CCB_ACT_GELU_NEW = 3, CCB_ACT_GELU = 4,
+  CCB_ACT_ELU = 5, CCB_ACT_SELU = 6, CCB_ACT_TANH = 7
+};
+enum { CCB_GEN_GREEDY = 0, CCB_GEN_SAMPLE = 1, CCB_GEN_BEAM = 2 };
+
+typedef struct ccb_model_desc {
+  /* language model: lms/GPT2.py:6-19 (HF GPT2LMHeadModel) or lms/GPTJ.py:5-18 (HF GPTJForCausalLM) */
+  int32_t lm_arch, lm_d, lm_layers, lm_heads, lm_vocab, lm_n_pos, lm_rotary_dim;
+  float lm_ln_eps;
+  /* prefix mapper: layers/Transformer.py:133-161 (TransformerMapper); MLP = upstream ClipCap MLP mapper */
+  int32_t map_kind, map_dim_clip, map_clip_len, map_prefix_len, map_heads, map_layers, map_hidden, map_act;
+  /* image encoder: OpenAI CLIP VisionTransformer (call sites inference.py:311, evaluate_model.py:359) */
+  int32_t vit_present, vit_image, vit_patch, vit_width, vit_layers, vit_heads, vit_out;
+  /* capacity */
+  int32_t max_images;      /* images (sequences before beam expansion) per call */
+  int32_t max_beam;        /* >= 1 */
+  int32_t max_ctx;         /* prefix + generated tokens per sequence */
+  int32_t max_lm_tokens;   /* max B*S of one ccb_lm_forward call */
+  int32_t page_tokens;     /* KV page size for greedy / sampling (beam search uses token-granular pages) */
+} ccb_model_desc;
+
+typedef struct ccb_gen_params {
+  int32_t mode;              /* CCB_GEN_* */
+  int32_t max_new_tokens;    /* entry_length (inference.py:77) / max_decode_length (evaluate_model.py:109) */
+  int32_t stop_token;        /* tokenizer.encode('.')[0] = 13 for GPT-2; < 0 disables stopping */
+  int32_t max_stops;         /* 1 = inference.py:284; 3 = evaluate_model.py:169-172 */
+  int32_t eos_token;         /* special id that always terminates (evaluate_model.py:171); < 0 = none */
+  float temperature;
+  float top_p;               /* <= 0 disables */
+  int32_t top_k;             /* <= 0 disables */
+  float repetition_penalty;  /* 1.0 disables (inference.py:53-57) */
+  int32_t beam_size;         /* inference.py:76 */
+  uint64_t seed;             /* Philox seed when q_noise == NULL */
+  const float* q_noise;      /* optional Exp(1) noise [max_new_tokens, N, q_ld] (torch.multinomial contract) */
+  int64_t q_ld;
+  const int64_t* row_ids;    /* optional global image ids [N] keying the Philox stream (multi-GPU invariance) */
+  const float* top_p_rows;   /* optional per-row top_p [N] (sampling.py:146-148) */
+  const int32_t* top_k_rows; /* optional per-row top_k [N] (sampling.py:135-145) */
+} ccb_gen_params;
+
+/* ---- lifetime ------------------------------------------------------------------------------------------ */
+CCB_API int ccb_create(ccb_ctx** out, const ccb_model_desc* desc, int device);
+CCB_API void ccb_destroy(ccb_ctx* ctx);
+CCB_API const char* ccb_last_error(const ccb_ctx* ctx);
+/* bytes of device memory held by the context (weights + KV pages + workspaces) */
+CCB_API int64_t ccb_device_bytes(const ccb_ctx* ctx);
+
+/* ---- weights ------------------------------------------------------------------------------------------- */
+/* Ingest one state_dict tensor (names as in SURVEY.md appendix B.3 under "clip_project.", "language_model.",
+ * "visual_encoder." / "visual."): copies + repacks to bf16 K-major (Conv1D [in,out] is transposed), LN / bias
+ * to f32.  The caller keeps its tensor.  Returns 1 if the name is not used by this context (ignored). */
+CCB_API int ccb_load_weight(ccb_ctx* ctx, const char* name, const void* dev_ptr, int dtype, const int64_t* shape, int ndim,
+                    void* stream);
+/* 0 when every weight the context needs has been loaded; otherwise -1 and ccb_last_error names one missing */
+CCB_API int ccb_weights_complete(ccb_ctx* ctx);
+
+/* ---- the hot path, stage by stage ---------------------------------------------------------------------- */
+/* clip_model.encode_image(image) (inference.py:311) / model.visual_encoder(image_tensor)
+ * (evaluate_model.py:359): images [B,3,H,W] NCHW -> feat_out [B, vit_out] f32 */
+CCB_API int ccb_vit_encode(ccb_ctx* ctx, const void* images, int dtype, int B, float* feat_out, void* stream);
+/* model.clip_project(prefix) (inference.py:312, model.py:137; layers/Transformer.py:153-161):
+ * feat [B, map_dim_clip] f32 -> prefix_out [B, map_prefix_len, lm_d] f32 */
+CCB_API int ccb_map_prefix(ccb_ctx* ctx, const float* feat, int B, float* prefix_out, void* stream);
+/* language_model.get_embedding_text(tokens) (lms/GPT2.py:14-15): out [n, lm_d] f32 */
+CCB_API int ccb_embed_tokens(ccb_ctx* ctx, const int32_t* tokens, int n, float* out, void* stream);
+/* language_model.call(inputs_embeds=E[, attention_mask]) (lms/GPT2.py:17-19 -> HF forward):
+ * embeds [B,S,lm_d] f32 -> logits [B,S,ld_logits] (last_only = 0) or [B,ld_logits] for the last position.
+ * key_mask: optional [B,S] uint8 (1 = attend), the HF attention_mask on keys; NULL = no mask. */
+CCB_API int ccb_lm_forward(ccb_ctx* ctx, const float* embeds, int B, int S, const uint8_t* key_mask, float* logits_out,
+                   int64_t ld_logits, int last_only, void* stream);
+/* generate_beam / generate_no_beam loops (inference.py:70-148, 219-292; evaluate_model.py:104-179), batched
+ * per row, the whole loop on the device: embeds [N,S0,lm_d] f32 prefix embeddings (what the reference loops
+ * receive as `embeds`, already including any text-prefix / BOS embedding).
+ *   greedy / sample: tokens_out [N, max_new_tokens] int32, lengths_out [N], scores_out ignored (may be NULL)
+ *   beam: tokens_out [N, beam, max_new_tokens], lengths_out [N, beam] (seq_lengths), scores_out [N, beam]
+ *         (scores / seq_lengths, inference.py:138); the caller picks argmax like inference.py:143-144. */
+CCB_API int ccb_generate(ccb_ctx* ctx, const ccb_gen_params* params, const float* embeds, int N, int S0, int32_t* tokens_out,
+                 int32_t* lengths_out, float* scores_out, void* stream);
+/* images -> captions in one call: ccb_vit_encode + ccb_map_prefix (+ BOS embedding appended when
+ * append_bos >= 0, evaluate_model.py:124-133) + ccb_generate.  Same outputs as ccb_generate. */
+CCB_API int ccb_caption_images(ccb_ctx* ctx, const ccb_gen_params* params, const void* images, int dtype, int N,
+                       int append_bos, int32_t* tokens_out, int32_t* lengths_out, float* scores_out, void* stream);
+/* number of kernels launched by the library on this context since creation (CUDA-graph replays count the
+ * kernels inside the graph) */
+CCB_API int64_t ccb_launch_count(const ccb_ctx* ctx);
+/* last generate call: device time (ms) of prefill and of the decode loop measured with events on `stream`;
+ * valid after the stream has been synchronised. Returns 0 on success. */
+CCB_API int ccb_last_timing(ccb_ctx* ctx, float* prefill_ms, float* decode_ms, int* decode_steps);
+
+/* ---- logit processors and samplers on caller tensors ---------------------------------------------------- */
+/* sampling.py:114-162 top_k_top_p_filtering_batch (+ :65-69 repetition_penalty_apply, temperature) followed by
+ * softmax + torch.multinomial(p, 1|2) == argmax(p / q).  logits [B, ld] f32 (not modified).
+ * history [B, ld_hist] int32 with hist_len tokens per row (NULL = none).  q_noise [B, q_ld] or NULL (Philox).
+ * filtered_out: optional [B, ld] f32 receiving the masked logits (-inf = removed).  next_out [B] int32;
+ * alt_out optional [B] int32 = second draw without replacement (sampling.py:223). */
+CCB_API int ccb_sample(ccb_ctx* ctx, const float* logits, int64_t ld, int B, int V, const ccb_gen_params* params,
+               const int32_t* history, int64_t ld_hist, int hist_len, int step, float* filtered_out,
+               int32_t* next_out, int32_t* alt_out, void* stream);
+/* argmax with lowest-index tie rule (generate_beam with beam_size=1) */
+CCB_API int ccb_argmax(ccb_ctx* ctx, const float* logits, int64_t ld, int B, int V, int32_t* next_out, void* stream);
+/* one beam-search step on caller state (inference.py:98-131): logits [N*beam, ld] (step 0: [N, ld]);
+ * scores/seq_lengths [N,beam] f32, has_stopped [N,beam] uint8, tokens [N,beam,max_len] int32 updated in place;
+ * next_tokens / src_rows [N*beam] int32 out. */
+CCB_API int ccb_beam_step(ccb_ctx* ctx, const float* logits, int64_t ld, int N, int beam, int V, float temperature,
+                  int stop_token, int step, float* scores, float* seq_lengths, uint8_t* has_stopped,
+                  int32_t* tokens, int max_len, int32_t* next_tokens, int32_t* src_rows, void* stream);
+
+/* ---- single operators on caller tensors (used by the parity tests and micro-benchmarks) ------------------ */
+/* out[t, f] = act(sum_k x[t,k] * w[f,k] + bias[f]) + residual[t, f]; x [tokens, K] bf16 (ld lda), w [features, K]
+ * bf16, bias f32 or NULL, residual f32 [tokens, ldr] or NULL, out f32 or bf16 [tokens, ldo].
+ * orientation: 0 auto, 1 normal (tokens on the 128-row MMA side), 2 swapped (weights on the 128-row side). */
+CCB_API int ccb_op_linear(ccb_ctx* ctx, const void* x, int64_t lda, int tokens, const void* w, int features, int K,
+                  const float* bias, int act, const float* residual, int64_t ldr, void* out, int64_t ldo,
+                  int out_bf16, int orientation, int bn, int split_k, void* stream);
+/* y = LayerNorm(x) over the last dim: x f32 [rows, d] -> y bf16 [rows, d] */
+CCB_API int ccb_op_layernorm(ccb_ctx* ctx, const float* x, const float* gamma, const float* beta, float eps, void* y_bf16,
+                     int rows, int d, void* stream);
+/* softmax(q k^T * scale [causal]) v for a fused qkv buffer [B*S, 3*H*hd] bf16 -> out [B*S, H*hd] bf16 */
+CCB_API int ccb_op_attention(ccb_ctx* ctx, const void* qkv_bf16, void* out_bf16, int B, int S, int H, int hd, float scale,
+                     int causal, int rotary_dim, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLIPCAP_B200_H_ */
