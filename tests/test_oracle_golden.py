@@ -1,0 +1,137 @@
+"""Pins oracle/clipcap_oracle.py against the fixtures produced by running the reference itself
+(tools/make_golden.py -> tests/golden/*.pt).  CPU only."""
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import clipcap_oracle as orc  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def load(name):
+    return torch.load(os.path.join(GOLDEN, name), weights_only=False)
+
+
+def f32(sd):
+    return {k: (v.float() if v.is_floating_point() else v) for k, v in sd.items()}
+
+
+def close(a, b, rel=2e-5):
+    return (a - b).abs().max().item() <= rel * max(b.abs().max().item(), 1e-6)
+
+
+@pytest.fixture(scope="module", params=["gpt2", "gptj"])
+def fx(request):
+    f = load("tiny_%s.pt" % request.param)
+    f["lm"] = orc.OracleLM(f32(f["sd_lm"]), f["arch"], f["heads"], f["rotary_dim"])
+    f["sd_mapper32"] = f32(f["sd_mapper"])
+    f["sd_vit32"] = f32(f["sd_vit"])
+    return f
+
+
+def test_vit_matches_reference(fx):
+    feat = orc.vit_forward(fx["sd_vit32"], fx["images"], fx["vit_heads"], fx["vit_patch"])
+    assert close(feat, fx["feat"])
+
+
+def test_mapper_matches_reference(fx):
+    prefix = orc.mapper_forward(fx["sd_mapper32"], fx["feat"], fx["CL"], fx["map_heads"])
+    assert close(prefix, fx["prefix"])
+
+
+def test_lm_call_matches_reference(fx):
+    assert close(fx["lm"].logits(fx["prefix"]), fx["logits_prefix"], 5e-5)
+
+
+def test_lm_cached_equals_full(fx):
+    lm = fx["lm"]
+    full = lm.logits(fx["prefix"])
+    first, past = lm.forward(fx["prefix"][:, :3])
+    rest, _ = lm.forward(fx["prefix"][:, 3:], past=past)
+    assert close(torch.cat((first, rest), 1), full, 5e-5)
+
+
+def test_caption_model_forward_matches_reference(fx):
+    mapper = lambda feat: orc.mapper_forward(fx["sd_mapper32"], feat, fx["CL"], fx["map_heads"])
+    logits = orc.caption_model_forward(fx["lm"], mapper, fx["tokens"], fx["feat"], fx["mask"])
+    assert close(logits, fx["logits_tf"], 5e-5)
+
+
+@pytest.mark.parametrize("use_cache", [False, True])
+@pytest.mark.parametrize("key,beam,T,temp", [("greedy", 1, 10, 1.0), ("beam5", 5, 10, 1.0), ("beam3_T2", 3, 8, 2.0)])
+def test_generate_beam_matches_reference(fx, key, beam, T, temp, use_cache):
+    for i, want in enumerate(fx[key]):
+        tokens, lens, scores, order = orc.generate_beam(fx["lm"], fx["prefix"][i:i + 1], beam, T, temp, fx["stop_id"], use_cache)
+        best = int(order[0])
+        assert tokens[best, :int(lens[best])].tolist() == want
+
+
+def _replay(seed, V):
+    g = torch.Generator().manual_seed(seed)
+    # torch.multinomial draws q = empty_like(p).exponential_(1) from the same stream, one [V] tensor per call
+    return lambda ci, step: torch.empty(V).exponential_(1, generator=g)
+
+
+def test_generate_no_beam_inference_matches_reference(fx):
+    for i, want in enumerate(fx["nobeam_inference"]):
+        got = orc.generate_no_beam(fx["lm"], fx["prefix"][i:i + 1], [0.1 * k for k in range(1, 10)],
+                                   _replay(fx["nobeam_inference_seeds"][i], fx["V"]), entry_length=8, stop_token=fx["stop_id"],
+                                   repetition_penalty=1.2)
+        assert got == want
+
+
+def test_generate_no_beam_evaluate_matches_reference(fx):
+    for i, want in enumerate(fx["nobeam_evaluate"]):
+        got = orc.generate_no_beam(fx["lm"], fx["prefix"][i:i + 1], [0.3, 0.9], _replay(fx["nobeam_seed"] + 100 + i, fx["V"]),
+                                   entry_length=8, stop_token=fx["stop_id"], repetition_penalty=1.2, max_stops=2,
+                                   special_ids=[fx["V"] - 1], bos_token=fx["V"] - 1, use_cache=True)
+        assert got == want
+
+
+def test_greedy_batched_equals_per_image(fx):
+    toks, lens = orc.generate_greedy(fx["lm"], fx["prefix"], 10, fx["stop_id"])
+    for i, want in enumerate(fx["greedy"]):
+        assert toks[i, :int(lens[i])].tolist() == want
+
+
+# ---------------------------------------------------------------------------------------------- logit processors
+@pytest.fixture(scope="module")
+def sx():
+    return load("sampler.pt")
+
+
+def same(a, b):
+    return torch.equal(torch.isinf(a), torch.isinf(b)) and torch.equal(torch.nan_to_num(a, neginf=0.0), torch.nan_to_num(b, neginf=0.0))
+
+
+def test_batch_filters_match_reference(sx):
+    L = sx["logits"]
+    assert same(orc.top_k_top_p_filtering_batch(L, 0, 0.9), sx["topp_0.9"])
+    assert same(orc.top_k_top_p_filtering_batch(L, 0, 0.1), sx["topp_0.1"])
+    assert same(orc.top_k_top_p_filtering_batch(L, 40, 0.0), sx["topk_40"])
+    assert same(orc.top_k_top_p_filtering_batch(L, 0.05, 0.0), sx["topk_0.05"])
+    assert same(orc.top_k_top_p_filtering_batch(L, 40, 0.5), sx["topk_40_topp_0.5"])
+    assert same(orc.top_k_top_p_filtering_batch(L, sx["top_k_rows"].clone(), sx["top_p_rows"].clone()), sx["rows"])
+
+
+def test_1d_filters_and_penalty_match_reference(sx):
+    L = sx["logits"]
+    for i in range(L.shape[0]):
+        assert same(orc.top_k_top_p_filtering(L[i], 0, 0.8), sx["topp1d_0.8"][i])
+        assert same(orc.top_k_top_p_filtering(L[i], 7, 0.0), sx["topk1d_7"][i])
+    assert torch.equal(orc.repetition_penalty_apply(L, sx["history"], 1.2), sx["rep_1.2"])
+    assert torch.equal(orc.repetition_penalty_apply(L[0], sx["history"][0], 1.2), sx["rep_1.2_inference_row0"])
+
+
+def test_multinomial_identity(sx):
+    probs = torch.softmax(sx["topp_0.9"], -1)
+    g = torch.Generator().manual_seed(sx["multinomial_seed"])
+    q1 = torch.empty_like(probs).exponential_(1, generator=g)
+    q2 = torch.empty_like(probs).exponential_(1, generator=g)
+    assert torch.equal(orc.multinomial_from_noise(probs, q1, 1), sx["multinomial_1"])
+    assert torch.equal(orc.multinomial_from_noise(probs, q2, 2), sx["multinomial_2"])

@@ -1,0 +1,231 @@
+"""Generates tests/golden/*.pt by RUNNING THE REFERENCE ITSELF (build container only).
+
+    PYTHONDONTWRITEBYTECODE=1 python tools/make_golden.py
+
+The reference (/root/reference) has no tests or golden vectors, so the fixtures are the outputs of its own,
+unmodified modules -- layers.TransformerMapper, lms.GPT2 / lms.GPTJ (HF transformers), model.CLIPCaptionModel,
+inference.generate_beam / generate_no_beam / top_k_top_p_filtering / repetition_penalty_apply,
+evaluate_model.generate_no_beam, sampling.top_k_top_p_filtering_batch / repetition_penalty_apply -- on seeded
+tiny models whose weights are rounded to bf16 once (the comparand both sides share).  The OpenAI `clip` package
+is not installed; HF CLIPVisionModelWithProjection (same arithmetic) stands in and its
+weights are exported under the OpenAI names.  The fixtures hold weights + inputs + outputs, so the tests that
+consume them (tests/test_oracle_golden.py on CPU, tests/test_gpu_parity.py on the B200) never need the reference.
+"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import ref_harness  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def bf16_round_(module):
+    with torch.no_grad():
+        for p in module.parameters():
+            p.copy_(p.bfloat16().float())
+    return module
+
+
+def export_clip_vision(hf):
+    """HF CLIPVisionModelWithProjection -> OpenAI `visual.*` names."""
+    s = hf.state_dict()
+    o = {}
+    o["conv1.weight"] = s["vision_model.embeddings.patch_embedding.weight"]
+    o["class_embedding"] = s["vision_model.embeddings.class_embedding"]
+    o["positional_embedding"] = s["vision_model.embeddings.position_embedding.weight"]
+    o["ln_pre.weight"] = s["vision_model.pre_layrnorm.weight"]
+    o["ln_pre.bias"] = s["vision_model.pre_layrnorm.bias"]
+    o["ln_post.weight"] = s["vision_model.post_layernorm.weight"]
+    o["ln_post.bias"] = s["vision_model.post_layernorm.bias"]
+    o["proj"] = s["visual_projection.weight"].t().contiguous()
+    n = hf.config.num_hidden_layers
+    for l in range(n):
+        a = "vision_model.encoder.layers.%d." % l
+        b = "transformer.resblocks.%d." % l
+        o[b + "ln_1.weight"], o[b + "ln_1.bias"] = s[a + "layer_norm1.weight"], s[a + "layer_norm1.bias"]
+        o[b + "ln_2.weight"], o[b + "ln_2.bias"] = s[a + "layer_norm2.weight"], s[a + "layer_norm2.bias"]
+        o[b + "attn.in_proj_weight"] = torch.cat([s[a + "self_attn.%s_proj.weight" % n_] for n_ in "qkv"], 0)
+        o[b + "attn.in_proj_bias"] = torch.cat([s[a + "self_attn.%s_proj.bias" % n_] for n_ in "qkv"], 0)
+        o[b + "attn.out_proj.weight"], o[b + "attn.out_proj.bias"] = s[a + "self_attn.out_proj.weight"], s[a + "self_attn.out_proj.bias"]
+        o[b + "mlp.c_fc.weight"], o[b + "mlp.c_fc.bias"] = s[a + "mlp.fc1.weight"], s[a + "mlp.fc1.bias"]
+        o[b + "mlp.c_proj.weight"], o[b + "mlp.c_proj.bias"] = s[a + "mlp.fc2.weight"], s[a + "mlp.fc2.bias"]
+    return {k: v.detach().clone() for k, v in o.items()}
+
+
+class TokenizerStub:
+    """The tokenizer surface the generate loops touch (lms/GPT2.py:22-48); ids in, ids out."""
+
+    def __init__(self, stop_id, bos=None, special=()):
+        self.stop_id = stop_id
+        self.bos_token_id = bos
+        self.all_special_ids = list(special)
+
+    def encode_text(self, text, *a, **k):
+        return [self.stop_id]
+
+    def decode_tokens(self, tokens):
+        return [int(t) for t in tokens]
+
+
+def pack_sd(sd):
+    return {k: v.detach().bfloat16() if v.is_floating_point() else v.detach().clone() for k, v in sd.items()}
+
+
+def make_model_fixture(ref, arch, seed):
+    from transformers import CLIPVisionConfig, CLIPVisionModelWithProjection, GPT2Config, GPTJConfig
+    torch.manual_seed(seed)
+    V, d, heads, P, CL, dim_clip = 503, 128, 2, 4, 4, 64
+    vit_cfg = CLIPVisionConfig(hidden_size=64, intermediate_size=256, num_hidden_layers=2, num_attention_heads=2,
+                               image_size=64, patch_size=32, projection_dim=dim_clip, hidden_act="quick_gelu")
+    vit = bf16_round_(CLIPVisionModelWithProjection(vit_cfg).eval())
+    if arch == "gpt2":
+        lm = ref.lms.GPT2(GPT2Config(vocab_size=V, n_positions=64, n_embd=d, n_layer=2, n_head=heads))
+        # HF's 0.02 init makes a 2-layer tied-embedding model echo its input token; larger block weights make
+        # the layers matter and a peakier embedding keeps top-1 margins above bf16 noise
+        with torch.no_grad():
+            lm.transformer.wte.weight.mul_(4.0)
+            for n_, p_ in lm.transformer.h.named_parameters():
+                if p_.dim() == 2:
+                    p_.mul_(6.0)
+    else:
+        V = 520
+        lm = ref.lms.GPTJ(GPTJConfig(vocab_size=V, n_positions=64, n_embd=d, n_layer=2, n_head=heads, rotary_dim=16))
+        with torch.no_grad():
+            lm.transformer.wte.weight.mul_(4.0)
+            lm.lm_head.weight.mul_(8.0)
+            lm.lm_head.bias.normal_(0, 0.1)
+            for n_, p_ in lm.transformer.h.named_parameters():
+                if p_.dim() == 2:
+                    p_.mul_(6.0)
+    lm = bf16_round_(lm.eval())
+    stop_id = 13
+    tok = TokenizerStub(stop_id, bos=V - 1, special=[V - 1])
+
+    class VisualEncoder(torch.nn.Module):  # stands in for clip_model.visual / encode_image
+        def __init__(self, m):
+            super().__init__()
+            self.m = m
+
+        def forward(self, x):
+            return self.m(pixel_values=x).image_embeds
+
+    model = ref.model.CLIPCaptionModel(
+        language_model=lm, tokenizer=tok, visual_encoder=VisualEncoder(vit), validator=None,
+        train_visual_encoder=False, use_all_vit_features=False, prefix_size=dim_clip, prefix_length=P,
+        clip_prefix_length=CL, num_attention_heads=8, num_layers=2, mlp_ratio=4.0, prefix_init_std=1.0,
+        act_fn_name="relu", pos_embeddings=False)
+    bf16_round_(model.clip_project)
+    model.eval()
+
+    N = 3
+    images = torch.randn(N, 3, 64, 64)
+    fx = {"arch": arch, "V": V, "d": d, "heads": heads, "P": P, "CL": CL, "dim_clip": dim_clip, "map_heads": 8,
+          "rotary_dim": 16 if arch == "gptj" else 0, "vit_heads": 2, "vit_patch": 32, "vit_image": 64, "vit_width": 64,
+          "vit_layers": 2, "images": images}
+    with torch.no_grad():
+        feat = model.visual_encoder(images).float()                       # encode_image (inference.py:311)
+        prefix = model.clip_project(feat)                                 # inference.py:312
+        tokens = torch.randint(0, V - 1, (N, 6))
+        mask = torch.ones(N, 6, dtype=torch.bool)
+        mask[1, 4:] = False
+        mask[2, 2:] = False
+        logits_tf = model(tokens, feat, mask).logits                      # model.py:132-149
+        logits_prefix = lm.call(inputs_embeds=prefix).logits              # lms/GPT2.py:17-19
+        fx.update(feat=feat, prefix=prefix, tokens=tokens, mask=mask, logits_tf=logits_tf, logits_prefix=logits_prefix)
+
+        # choose the stop id so that stopping actually happens: the most frequent token of a free-running greedy decode
+        tok.stop_id = -1
+        free = [ref.inference.generate_beam(model, tok, prefix[i:i + 1], beam_size=1, entry_length=10)[0] for i in range(N)]
+        flat = [t for seq in free for t in seq[3:]]
+        tok.stop_id = max(set(flat), key=flat.count)
+        fx["stop_id"] = tok.stop_id
+        fx["greedy"] = [ref.inference.generate_beam(model, tok, prefix[i:i + 1], beam_size=1, entry_length=10)[0] for i in range(N)]
+        fx["beam5"] = [ref.inference.generate_beam(model, tok, prefix[i:i + 1], beam_size=5, entry_length=10)[0] for i in range(N)]
+        fx["beam3_T2"] = [ref.inference.generate_beam(model, tok, prefix[i:i + 1], beam_size=3, entry_length=8, temperature=2.0)[0] for i in range(N)]
+
+        # nucleus sampling, both variants; the global RNG is seeded so the oracle can replay the Exp(1) draws
+        fx["nobeam_seed"] = 1234 + seed
+        import contextlib
+        import io
+        outs, seeds = [], []
+        for i in range(N):
+            # inference.py:287 crashes on a one-token caption (`tokens.squeeze()` is 0-d): such seeds are skipped
+            s_i = fx["nobeam_seed"] + i
+            while True:
+                torch.manual_seed(s_i)
+                try:
+                    with contextlib.redirect_stdout(io.StringIO()):
+                        outs.append(ref.inference.generate_no_beam(model, tok, prefix[i:i + 1], entry_length=8, repetition_penalty=1.2))
+                    break
+                except TypeError:
+                    s_i += 1000
+            seeds.append(s_i)
+        fx["nobeam_inference"] = outs
+        fx["nobeam_inference_seeds"] = seeds
+        outs = []
+        for i in range(N):
+            torch.manual_seed(fx["nobeam_seed"] + 100 + i)
+            outs.append(ref.evaluate_model.generate_no_beam(model, prefix[i:i + 1], top_p_values=[0.3, 0.9],
+                                                            max_decode_length=8, repetition_penalty=1.2, max_stops=2))
+        fx["nobeam_evaluate"] = outs
+    fx["sd_lm"] = pack_sd(lm.state_dict())
+    fx["sd_mapper"] = pack_sd(model.clip_project.state_dict())
+    fx["sd_vit"] = pack_sd(export_clip_vision(vit))
+    return fx
+
+
+def make_sampler_fixture(ref, seed):
+    torch.manual_seed(seed)
+    B, V = 6, 1031
+    logits = torch.randn(B, V) * 3.0
+    logits[2, 5] = logits[2, 77] = logits[2].max() + 1.0            # exact ties at the top
+    logits[4] = torch.round(logits[4])                               # many ties everywhere
+    fx = {"logits": logits}
+    f = ref.sampling.top_k_top_p_filtering_batch
+    fx["topp_0.9"] = f(logits.clone(), top_k=0, top_p=0.9)
+    fx["topp_0.1"] = f(logits.clone(), top_k=0, top_p=0.1)
+    fx["topk_40"] = f(logits.clone(), top_k=40, top_p=0.0)
+    fx["topk_0.05"] = f(logits.clone(), top_k=0.05, top_p=0.0)
+    fx["topk_40_topp_0.5"] = f(logits.clone(), top_k=40, top_p=0.5)
+    tp = torch.tensor([0.1, 0.3, 0.5, 0.7, 0.9, 0.95])
+    tk = torch.tensor([0, 1, 5, 50, 0, 2000])
+    fx["top_p_rows"], fx["top_k_rows"] = tp, tk
+    fx["rows"] = f(logits.clone(), top_k=tk.clone(), top_p=tp.clone())
+    hist = torch.randint(0, V, (B, 7))
+    hist[0, 3] = hist[0, 1]                                           # duplicate ids in the history
+    fx["history"] = hist
+    fx["rep_1.2"] = ref.sampling.repetition_penalty_apply(logits.clone(), hist, 1.2)
+    fx["rep_1.2_inference_row0"] = ref.inference.repetition_penalty_apply(logits[0].clone(), hist[0], 1.2)
+    fx["topp1d_0.8"] = torch.stack([ref.inference.top_k_top_p_filtering(logits[i].clone(), top_p=0.8, top_k=0) for i in range(B)])
+    fx["topk1d_7"] = torch.stack([ref.evaluate_model.top_k_top_p_filtering(logits[i].clone(), top_p=0.0, top_k=7) for i in range(B)])
+    # torch.multinomial draws (n = 1 and n = 2 without replacement) with a seeded generator
+    probs = torch.softmax(fx["topp_0.9"], -1)
+    g = torch.Generator().manual_seed(99)
+    fx["multinomial_seed"] = 99
+    fx["multinomial_1"] = torch.multinomial(probs, 1, generator=g)
+    fx["multinomial_2"] = torch.multinomial(probs, 2, replacement=False, generator=g)
+    return fx
+
+
+def main():
+    ref = ref_harness.load_reference()
+    os.makedirs(OUT, exist_ok=True)
+    for arch, seed in (("gpt2", 11), ("gptj", 12)):
+        fx = make_model_fixture(ref, arch, seed)
+        path = os.path.join(OUT, "tiny_%s.pt" % arch)
+        torch.save(fx, path)
+        print(path, os.path.getsize(path) // 1024, "KiB", "stop_id", fx["stop_id"])
+        for k in ("greedy", "beam5", "beam3_T2", "nobeam_inference", "nobeam_evaluate"):
+            print("  ", k, fx[k])
+    fx = make_sampler_fixture(ref, 21)
+    path = os.path.join(OUT, "sampler.pt")
+    torch.save(fx, path)
+    print(path, os.path.getsize(path) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()
