@@ -44,7 +44,8 @@ __global__ void __launch_bounds__(kPrefillWarps * 32) attention_prefill_kernel(
   const int kstride = hw + 1;
   uint32_t* Ks = smem_u;
   uint32_t* Vs = Ks + S * kstride;
-  float* qbuf = reinterpret_cast<float*>(Vs + S * hw);           // [warps][hd]
+  // q rows are read back as float2: keep the fp32 region 8-byte aligned (S * (2 * hw + 1) words can be odd)
+  float* qbuf = reinterpret_cast<float*>(smem_u + ((S * (kstride + hw) + 1) & ~1));  // [warps][hd]
   float* pbuf = qbuf + kPrefillWarps * hd;                        // [warps][S]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bf16* base = qkv + static_cast<size_t>(b) * S * 3 * d;
@@ -286,7 +287,7 @@ int attention_prefill(const bf16* qkv, bf16* out, int B, int S, int H, int hd, f
                       const uint8_t* key_mask, cudaStream_t s) {
   if (B <= 0 || S <= 0) return 0;
   if (S > 256 || hd % 2) return (int)cudaErrorInvalidValue;
-  const size_t smem = (static_cast<size_t>(S) * (hd / 2 + 1) + static_cast<size_t>(S) * (hd / 2)) * 4 +
+  const size_t smem = (static_cast<size_t>(S) * (hd / 2 + 1) + static_cast<size_t>(S) * (hd / 2) + 1) * 4 +
                       static_cast<size_t>(kPrefillWarps) * (hd + S) * 4;
   if (smem > 200 * 1024) return (int)cudaErrorInvalidValue;
   static size_t configured = 0;

@@ -453,7 +453,8 @@ int generate_on_work_stream(ccb_ctx* c, const ccb_gen_params* p, const float* em
   RUN(launch_check());
   CUDA_OK(cudaMemsetAsync(c->gen_tokens, 0, sizeof(int) * static_cast<size_t>(rows) * T, s));
 
-  CUDA_OK(cudaEventRecord(c->ev_t0, s));
+  const int slot = static_cast<int>(c->generate_calls % ccb_ctx::kTimingSlots);
+  CUDA_OK(cudaEventRecord(c->ev_t0[slot], s));
   // ---- prefill: one pass over the prefix, K/V written to the cache, logits of the last position
   if (lm_prefill_layers(c, embeds, N, S0, nullptr, true, s)) return -1;
   if (lm_logits(c, N, S0, 1, c->logits, c->ldv, s)) return -1;
@@ -462,7 +463,7 @@ int generate_on_work_stream(ccb_ctx* c, const ccb_gen_params* p, const float* em
   } else {
     if (select_step(c, p, rows, T, true, s)) return -1;
   }
-  CUDA_OK(cudaEventRecord(c->ev_t1, s));
+  CUDA_OK(cudaEventRecord(c->ev_t1[slot], s));
 
   // ---- decode: T-1 replays of one captured step (every kernel reads step / ctx_len from device memory)
   if (T > 1) {
@@ -497,9 +498,9 @@ int generate_on_work_stream(ccb_ctx* c, const ccb_gen_params* p, const float* em
       c->launches += it->second.nodes;
     }
   }
-  CUDA_OK(cudaEventRecord(c->ev_t2, s));
-  c->last_decode_steps = T - 1;
-  c->timing_valid = true;
+  CUDA_OK(cudaEventRecord(c->ev_t2[slot], s));
+  c->timing_steps[slot] = T - 1;
+  c->generate_calls++;
 
   // ---- results
   CUDA_OK(cudaMemcpyAsync(tokens_out, c->gen_tokens, sizeof(int) * static_cast<size_t>(rows) * T, cudaMemcpyDeviceToDevice, s));
@@ -549,8 +550,11 @@ void ccb_destroy(ccb_ctx* c) {
   for (auto& kvp : c->graphs) cudaGraphExecDestroy(kvp.second.exec);
   for (void* p : c->allocs) cudaFree(p);
   if (c->work) cudaStreamDestroy(c->work);
-  for (cudaEvent_t e : {c->ev_in, c->ev_out, c->ev_t0, c->ev_t1, c->ev_t2})
+  for (cudaEvent_t e : {c->ev_in, c->ev_out})
     if (e) cudaEventDestroy(e);
+  for (int i = 0; i < ccb_ctx::kTimingSlots; ++i)
+    for (cudaEvent_t e : {c->ev_t0[i], c->ev_t1[i], c->ev_t2[i]})
+      if (e) cudaEventDestroy(e);
   delete c;
 }
 
@@ -785,11 +789,18 @@ int ccb_create(ccb_ctx** out, const ccb_model_desc* desc, int device) {
   if (cudaStreamCreateWithFlags(&c->work, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreate(&c->ev_t0) != cudaSuccess || cudaEventCreate(&c->ev_t1) != cudaSuccess ||
-      cudaEventCreate(&c->ev_t2) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
+      cudaDeviceSynchronize() != cudaSuccess) {
     fail(nullptr, "ccb_create: stream / event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
     ccb_destroy(c);
     return -1;
+  }
+  for (int i = 0; i < ccb_ctx::kTimingSlots; ++i) {
+    if (cudaEventCreate(&c->ev_t0[i]) != cudaSuccess || cudaEventCreate(&c->ev_t1[i]) != cudaSuccess ||
+        cudaEventCreate(&c->ev_t2[i]) != cudaSuccess) {
+      fail(nullptr, "ccb_create: event creation failed");
+      ccb_destroy(c);
+      return -1;
+    }
   }
   *out = c;
   return 0;
@@ -905,16 +916,30 @@ int ccb_caption_images(ccb_ctx* c, const ccb_gen_params* p, const void* images, 
   return r;
 }
 
-int ccb_last_timing(ccb_ctx* c, float* prefill_ms, float* decode_ms, int* decode_steps) {
+int ccb_timing_sum(ccb_ctx* c, int n_calls, float* prefill_ms, float* decode_ms, int* decode_steps) {
   if (!c) return -1;
-  if (!c->timing_valid) return fail(c, "ccb_last_timing: no generate call yet");
+  if (n_calls <= 0 || n_calls > ccb_ctx::kTimingSlots || n_calls > c->generate_calls)
+    return fail(c, "ccb_timing_sum: n_calls=%d outside [1, min(%d, generate calls so far = %lld)]", n_calls,
+                ccb_ctx::kTimingSlots, c->generate_calls);
   float a = 0.f, b = 0.f;
-  CUDA_OK(cudaEventElapsedTime(&a, c->ev_t0, c->ev_t1));
-  CUDA_OK(cudaEventElapsedTime(&b, c->ev_t1, c->ev_t2));
+  int steps = 0;
+  for (int i = 1; i <= n_calls; ++i) {
+    const int slot = static_cast<int>((c->generate_calls - i) % ccb_ctx::kTimingSlots);
+    float x = 0.f, y = 0.f;
+    CUDA_OK(cudaEventElapsedTime(&x, c->ev_t0[slot], c->ev_t1[slot]));
+    CUDA_OK(cudaEventElapsedTime(&y, c->ev_t1[slot], c->ev_t2[slot]));
+    a += x;
+    b += y;
+    steps += c->timing_steps[slot];
+  }
   if (prefill_ms) *prefill_ms = a;
   if (decode_ms) *decode_ms = b;
-  if (decode_steps) *decode_steps = c->last_decode_steps;
+  if (decode_steps) *decode_steps = steps;
   return 0;
+}
+
+int ccb_last_timing(ccb_ctx* c, float* prefill_ms, float* decode_ms, int* decode_steps) {
+  return ccb_timing_sum(c, 1, prefill_ms, decode_ms, decode_steps);
 }
 
 // ---------------------------------------------------------------------------------- samplers on caller tensors
@@ -927,6 +952,7 @@ int ccb_sample(ccb_ctx* c, const float* logits, int64_t ld, int B, int V, const 
   sp.ld_hist = ld_hist;
   sp.hist_len_scalar = hist_len;
   sp.step_scalar = step;
+  sp.q_step_stride = 0;  // q_noise here is the [B, q_ld] draw of this one step
   sp.filtered_out = filtered_out;
   sp.alt_out = alt_out;
   RUN(sample_top_p(logits, ld, B, V, sp, next_out, static_cast<cudaStream_t>(stream)));

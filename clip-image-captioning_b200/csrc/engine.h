@@ -118,11 +118,14 @@ struct ccb_ctx {
 
   // ---- streams / graphs / accounting
   cudaStream_t work = nullptr;
-  cudaEvent_t ev_in = nullptr, ev_out = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_t2 = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  // ring of (start, prefill done, decode done) events, one slot per generate call
+  static constexpr int kTimingSlots = 64;
+  cudaEvent_t ev_t0[kTimingSlots] = {}, ev_t1[kTimingSlots] = {}, ev_t2[kTimingSlots] = {};
+  int timing_steps[kTimingSlots] = {};
+  long long generate_calls = 0;
   std::unordered_map<std::string, ccb::GraphEntry> graphs;
   int64_t launches = 0;
   bool capturing = false;
   int capture_launches = 0;
-  int last_decode_steps = 0;
-  bool timing_valid = false;
 };

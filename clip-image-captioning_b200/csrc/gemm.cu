@@ -140,8 +140,9 @@ int gemm_launch(const GemmArgs& a, const GemmWorkspace& w, cudaStream_t stream) 
   if (a.force_split) {
     split = a.force_split;
   } else if (tiles < w.num_sms) {
-    // fill the machine: enough K-splits that tiles*split ~ number of SMs, each split >= 4 k-blocks
-    split = (w.num_sms + tiles - 1) / tiles;
+    // fill the machine without spilling into a second wave (one CTA per SM): tiles * split <= number of SMs,
+    // each split >= 4 k-blocks
+    split = w.num_sms / tiles;
     const int max_by_k = p.k_blocks / 4 > 0 ? p.k_blocks / 4 : 1;
     if (split > max_by_k) split = max_by_k;
     if (split > 16) split = 16;

@@ -188,10 +188,24 @@ __global__ void __launch_bounds__(192, 1) gemm_bf16_tn_kernel(const __grid_const
         if (p.split_k > 1) {
 #pragma unroll
           for (int v = 0; v < 32; ++v) acc[v] = 0.f;
-          for (int s = 0; s < p.split_k; ++s) {
-            const float* src = ws_tile + static_cast<size_t>(s) * (BN * 128) + quad * 32 + lane;
+          // fixed summation order 0..S-1 (deterministic); loads of 4 splits are in flight together
+          for (int s0 = 0; s0 < p.split_k; s0 += 4) {
+            float t[4][32];
 #pragma unroll
-            for (int v = 0; v < 32; ++v) acc[v] += ptx::ldcg_f32(src + (c0 + v) * 128);
+            for (int u = 0; u < 4; ++u) {
+              if (s0 + u < p.split_k) {
+                const float* src = ws_tile + static_cast<size_t>(s0 + u) * (BN * 128) + quad * 32 + lane;
+#pragma unroll
+                for (int v = 0; v < 32; ++v) t[u][v] = ptx::ldcg_f32(src + (c0 + v) * 128);
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (s0 + u < p.split_k) {
+#pragma unroll
+                for (int v = 0; v < 32; ++v) acc[v] += t[u][v];
+              }
+            }
           }
         } else {
           uint32_t r[32];

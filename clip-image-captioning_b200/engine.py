@@ -139,6 +139,13 @@ class Engine:
         self._check(self.lib.ccb_last_timing(self._h, C.byref(a), C.byref(b), C.byref(n)))
         return a.value, b.value, n.value
 
+    def timing_sum(self, n_calls: int):
+        """(prefill_ms, decode_ms, decode_steps) summed over the last n_calls generate calls; synchronises."""
+        torch.cuda.synchronize(self.device)
+        a, b, n = C.c_float(), C.c_float(), C.c_int()
+        self._check(self.lib.ccb_timing_sum(self._h, n_calls, C.byref(a), C.byref(b), C.byref(n)))
+        return a.value, b.value, n.value
+
     # ------------------------------------------------------------------------------------------ weights
     def load_state_dict(self, sd: Dict[str, torch.Tensor], prefix: str = "", strict: bool = True):
         """Ingest tensors named as in the reference checkpoint (`language_model.*`, `clip_project.*`,

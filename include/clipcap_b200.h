@@ -124,6 +124,8 @@ CCB_API int64_t ccb_launch_count(const ccb_ctx* ctx);
 /* last generate call: device time (ms) of prefill and of the decode loop measured with events on `stream`;
  * valid after the stream has been synchronised. Returns 0 on success. */
 CCB_API int ccb_last_timing(ccb_ctx* ctx, float* prefill_ms, float* decode_ms, int* decode_steps);
+/* same, summed over the last n_calls generate calls (n_calls <= 64): total prefill ms, decode ms, decode steps */
+CCB_API int ccb_timing_sum(ccb_ctx* ctx, int n_calls, float* prefill_ms, float* decode_ms, int* decode_steps);
 
 /* ---- logit processors and samplers on caller tensors ---------------------------------------------------- */
 /* sampling.py:114-162 top_k_top_p_filtering_batch (+ :65-69 repetition_penalty_apply, temperature) followed by

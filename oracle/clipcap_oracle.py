@@ -238,6 +238,10 @@ def caption_model_forward(lm: OracleLM, mapper_fn, tokens, prefix, mask):
 
 
 # ------------------------------------------------------------------------------------------------ logit processors
+# Tie rule.  The reference sorts with torch.sort(descending=True), whose order among EQUAL logits is unspecified
+# (it differs between the CPU and CUDA back ends).  Which of several logits tied exactly at the nucleus boundary
+# survive is therefore not defined by the reference; the oracle pins it with a stable sort (lowest index first),
+# and so does the CUDA kernel.  Everything else (count kept, every non-tied element) is identical to the reference.
 def top_k_top_p_filtering(logits, top_k=0, top_p=0.0, filter_value=-float("inf")):
     """inference.py:24-51 / evaluate_model.py:67-94 (1-D).  Works on a copy."""
     logits = logits.clone()
@@ -246,7 +250,7 @@ def top_k_top_p_filtering(logits, top_k=0, top_p=0.0, filter_value=-float("inf")
     if top_k > 0:
         logits[logits < torch.topk(logits, top_k)[0][..., -1, None]] = filter_value
     if top_p > 0.0:
-        sorted_logits, sorted_indices = torch.sort(logits, descending=True)
+        sorted_logits, sorted_indices = torch.sort(logits, descending=True, stable=True)
         cumulative_probs = torch.cumsum(F.softmax(sorted_logits, dim=-1), dim=-1)
         remove = cumulative_probs > top_p
         remove[..., 1:] = remove[..., :-1].clone()
@@ -287,7 +291,7 @@ def top_k_top_p_filtering_batch(logits, top_k=0, top_p=0.0, filter_value=float("
     if (type(top_p) == float and top_p > 0.0) or (torch.is_tensor(top_p) and torch.any(top_p > 0)):
         if torch.is_tensor(top_p) and top_p.size(-1) != 1:
             top_p = top_p.unsqueeze(-1)
-        sorted_logits, sorted_indices = torch.sort(logits, descending=True, dim=-1)
+        sorted_logits, sorted_indices = torch.sort(logits, descending=True, dim=-1, stable=True)
         cumulative_probs = torch.cumsum(F.softmax(sorted_logits, dim=-1), dim=-1)
         remove = cumulative_probs > top_p
         remove[:, 1:] = remove[:, :-1].clone()
