@@ -138,145 +138,140 @@ __global__ void __launch_bounds__(kPrefillWarps * 32) attention_prefill_kernel(
 }
 
 // ------------------------------------------------------------------------------------------------ decode
-// CTA = 4 warps = one (row, head).  Lanes are grouped LPT = HD/8 per token (8 bf16 = 16 bytes per lane);
-// warp w visits token groups w, w+4, ...  Online softmax per lane-group; merged across groups and warps.
+// One WARP per (row, head); 4 warps per CTA.  The step is bound by the K/V bytes it has to read, so the kernel is
+// organised for memory-level parallelism: every lane owns whole tokens (t = lane, lane + 32, ...) and fetches their
+// 128..512-byte K (then V) rows with independent 16-byte loads (HD/8 in flight per token slot), instead of a few
+// lanes sharing one token behind a block-table lookup chain.
+//   pass 1: s_t = q . K_t for the lane's tokens (q pre-scaled, fp32 in shared memory, read as broadcasts)
+//   softmax statistics across the warp (+ the new token, whose k/v come from the qkv buffer, not the cache)
+//   pass 2: per 64-dim chunk, acc[64] += p_t * V_t over the lane's tokens, then a 62-shuffle transpose-reduce
+//           leaves dims (2*lane, 2*lane+1) of the chunk in each lane -> one coalesced 128-byte store per warp.
+constexpr int kDecodeWarps = 4;
+
 template <int HD>
-__global__ void __launch_bounds__(128) attention_decode_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out,
-                                                               int H, float scale, KvCache cache, int layer,
-                                                               const int* __restrict__ block_table,
-                                                               const int* __restrict__ ctx_len, int rotary_dim) {
-  constexpr int LPT = HD / 8;     // lanes per token
-  constexpr int TPW = 32 / LPT;   // tokens per warp iteration
-  const int h = blockIdx.x, b = blockIdx.y;
-  const int d = H * HD;
+__global__ void __launch_bounds__(kDecodeWarps * 32) attention_decode_kernel(
+    const bf16* __restrict__ qkv, bf16* __restrict__ out, int rows, int H, float scale, KvCache cache, int layer,
+    const int* __restrict__ block_table, const int* __restrict__ ctx_len, int rotary_dim, int sc_cap) {
+  constexpr int E = HD / 32;  // dims per lane in the "own dims" layout (2, 4, 8): pairs stay inside a lane
+  extern __shared__ float dsm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int grp = lane / LPT, sub = lane % LPT;
-  const int ctx = ctx_len[b];  // tokens already cached; the new token sits at position ctx
+  ptx::grid_dep_wait();
+  ptx::grid_dep_launch();
+  const int unit = blockIdx.x * kDecodeWarps + warp;  // (row, head)
+  if (unit >= rows * H) return;
+  const int b = unit / H, h = unit % H;
+  const int d = H * HD;
+  float* qs = dsm + warp * (HD + sc_cap);  // [HD] scaled query
+  float* sc = qs + HD;                      // [ctx] scores
+  const int ctx = ctx_len[b];               // tokens already cached; the new token sits at position ctx
   const bf16* row = qkv + static_cast<size_t>(b) * 3 * d;
   const int* bt = block_table + static_cast<size_t>(b) * cache.max_pages_per_row;
 
-  // this lane's 8 q values and the new token's k/v chunk
-  float q[8], kn[8], vn[8];
+  // ---- q / k_new / v_new for this lane's E dims; rotary on q and k_new; append k_new / v_new to the cache
+  float s_new = 0.f;
   {
-    const uint4 qu = *reinterpret_cast<const uint4*>(row + h * HD + sub * 8);
-    const uint4 ku = *reinterpret_cast<const uint4*>(row + d + h * HD + sub * 8);
-    const uint4 vu = *reinterpret_cast<const uint4*>(row + 2 * d + h * HD + sub * 8);
-    const uint32_t qa[4] = {qu.x, qu.y, qu.z, qu.w}, ka[4] = {ku.x, ku.y, ku.z, ku.w}, va[4] = {vu.x, vu.y, vu.z, vu.w};
+    float q[E], kn[E], vn[E];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      float2 a = unpack_bf16x2(qa[t]), k2 = unpack_bf16x2(ka[t]), v2 = unpack_bf16x2(va[t]);
-      if (rotary_dim > 0 && sub * 8 + 2 * t < rotary_dim) {
-        rotary_pair(a.x, a.y, sub * 4 + t, ctx, rotary_dim);
-        rotary_pair(k2.x, k2.y, sub * 4 + t, ctx, rotary_dim);
-        // keep the cached key bf16-rounded exactly as later steps will read it
-        k2 = unpack_bf16x2(pack_bf16x2(k2.x, k2.y));
+    for (int e = 0; e < E; e += 2) {
+      const int dim = lane * E + e;
+      float2 qf = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(row + h * HD + dim));
+      float2 kf = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(row + d + h * HD + dim));
+      const float2 vf = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(row + 2 * d + h * HD + dim));
+      if (rotary_dim > 0 && dim < rotary_dim) {
+        rotary_pair(qf.x, qf.y, dim / 2, ctx, rotary_dim);
+        rotary_pair(kf.x, kf.y, dim / 2, ctx, rotary_dim);
+        kf = unpack_bf16x2(pack_bf16x2(kf.x, kf.y));  // exactly what later steps read back from the cache
       }
-      q[2 * t] = a.x * scale; q[2 * t + 1] = a.y * scale;
-      kn[2 * t] = k2.x; kn[2 * t + 1] = k2.y;
-      vn[2 * t] = v2.x; vn[2 * t + 1] = v2.y;
+      q[e] = qf.x * scale; q[e + 1] = qf.y * scale;
+      kn[e] = kf.x; kn[e + 1] = kf.y;
+      vn[e] = vf.x; vn[e + 1] = vf.y;
     }
-  }
-  // append the new token's K/V to the cache (warp 0, first lane group)
-  if (warp == 0 && grp == 0) {
     const int page = bt[ctx / cache.page_tokens];
-    const int t = ctx % cache.page_tokens;
-    uint4 kp, vp;
-    kp.x = pack_bf16x2(kn[0], kn[1]); kp.y = pack_bf16x2(kn[2], kn[3]);
-    kp.z = pack_bf16x2(kn[4], kn[5]); kp.w = pack_bf16x2(kn[6], kn[7]);
-    vp.x = pack_bf16x2(vn[0], vn[1]); vp.y = pack_bf16x2(vn[2], vn[3]);
-    vp.z = pack_bf16x2(vn[4], vn[5]); vp.w = pack_bf16x2(vn[6], vn[7]);
-    *reinterpret_cast<uint4*>(cache.base + kv_index(cache, layer, 0, page, h, t) + sub * 8) = kp;
-    *reinterpret_cast<uint4*>(cache.base + kv_index(cache, layer, 1, page, h, t) + sub * 8) = vp;
-  }
-
-  float m = -INFINITY, l = 0.f, acc[8];
+    const int tin = ctx % cache.page_tokens;
+    bf16* kdst = cache.base + kv_index(cache, layer, 0, page, h, tin) + lane * E;
+    bf16* vdst = cache.base + kv_index(cache, layer, 1, page, h, tin) + lane * E;
 #pragma unroll
-  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-
-  // cached tokens [0, ctx); token ctx (the new one) is folded in by warp 0 / group 0 from registers
-  for (int t0 = warp * TPW; t0 < ctx; t0 += 4 * TPW) {
-    const int tok = t0 + grp;
-    const bool valid = tok < ctx;
-    uint4 ku = make_uint4(0, 0, 0, 0), vu = make_uint4(0, 0, 0, 0);
-    if (valid) {
-      const int page = bt[tok / cache.page_tokens];
-      const int t = tok % cache.page_tokens;
-      ku = ptx::ld_nc_u4(cache.base + kv_index(cache, layer, 0, page, h, t) + sub * 8);
-      vu = ptx::ld_nc_u4(cache.base + kv_index(cache, layer, 1, page, h, t) + sub * 8);
+    for (int e = 0; e < E; e += 2) {
+      *reinterpret_cast<uint32_t*>(kdst + e) = pack_bf16x2(kn[e], kn[e + 1]);
+      *reinterpret_cast<uint32_t*>(vdst + e) = pack_bf16x2(vn[e], vn[e + 1]);
+      qs[lane * E + e] = q[e];
+      qs[lane * E + e + 1] = q[e + 1];
+      s_new = fmaf(q[e], kn[e], s_new);
+      s_new = fmaf(q[e + 1], kn[e + 1], s_new);
     }
-    const uint32_t ka[4] = {ku.x, ku.y, ku.z, ku.w}, va[4] = {vu.x, vu.y, vu.z, vu.w};
+    s_new = warp_sum(s_new);
+  }
+  __syncwarp();
+
+  // ---- pass 1: scores of the cached tokens
+  float mx = s_new;
+  for (int t = lane; t < ctx; t += 32) {
+    const int page = bt[t / cache.page_tokens];
+    const uint4* kp = reinterpret_cast<const uint4*>(cache.base + kv_index(cache, layer, 0, page, h, t % cache.page_tokens));
+    uint4 kk[HD / 8];
+#pragma unroll
+    for (int c = 0; c < HD / 8; ++c) kk[c] = ptx::ld_nc_u4(kp + c);
     float s = 0.f;
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const float2 k2 = unpack_bf16x2(ka[t]);
-      s = fmaf(q[2 * t], k2.x, s);
-      s = fmaf(q[2 * t + 1], k2.y, s);
+    for (int c = 0; c < HD / 8; ++c) {
+      const float4 q0 = *reinterpret_cast<const float4*>(qs + c * 8);
+      const float4 q1 = *reinterpret_cast<const float4*>(qs + c * 8 + 4);
+      const float2 k0 = unpack_bf16x2(kk[c].x), k1 = unpack_bf16x2(kk[c].y), k2 = unpack_bf16x2(kk[c].z), k3 = unpack_bf16x2(kk[c].w);
+      s = fmaf(q0.x, k0.x, s); s = fmaf(q0.y, k0.y, s); s = fmaf(q0.z, k1.x, s); s = fmaf(q0.w, k1.y, s);
+      s = fmaf(q1.x, k2.x, s); s = fmaf(q1.y, k2.y, s); s = fmaf(q1.z, k3.x, s); s = fmaf(q1.w, k3.y, s);
     }
-#pragma unroll
-    for (int o = LPT / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (valid) {
-      const float mn = fmaxf(m, s);
-      const float corr = expf(m - mn);  // m = -inf on first use -> 0
-      const float p = expf(s - mn);
-      l = l * corr + p;
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const float2 v2 = unpack_bf16x2(va[t]);
-        acc[2 * t] = acc[2 * t] * corr + p * v2.x;
-        acc[2 * t + 1] = acc[2 * t + 1] * corr + p * v2.y;
-      }
-      m = mn;
-    }
+    sc[t] = s;
+    mx = fmaxf(mx, s);
   }
-  if (warp == 0 && grp == 0) {
-    float s = 0.f;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) s = fmaf(q[e], kn[e], s);
-#pragma unroll
-    for (int o = LPT / 2; o > 0; o >>= 1) s += __shfl_xor_sync((LPT == 32) ? 0xffffffffu : ((1u << LPT) - 1u), s, o);
-    const float mn = fmaxf(m, s);
-    const float corr = expf(m - mn);
-    const float p = expf(s - mn);
-    l = l * corr + p;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) acc[e] = acc[e] * corr + p * vn[e];
-    m = mn;
+  mx = warp_max(mx);
+  const float p_new = expf(s_new - mx);
+  float lsum = 0.f;
+  for (int t = lane; t < ctx; t += 32) {
+    const float p = expf(sc[t] - mx);
+    sc[t] = p;  // own slots only: no cross-lane hazard
+    lsum += p;
   }
+  lsum = warp_sum(lsum) + p_new;
+  const float inv = 1.f / lsum;
 
-  // merge the 4*TPW partial states: through shared memory, summed in a fixed order by the first LPT lanes
-  __shared__ float sm_m[4 * 32 / 1];
-  __shared__ float sm_l[4 * 32];
-  __shared__ float sm_acc[4 * 32 * 8];
-  const int slot = warp * 32 + lane;
-  sm_m[slot] = m;
-  sm_l[slot] = l;
+  // ---- pass 2: output, 64 dims at a time
+#pragma unroll 1
+  for (int c0 = 0; c0 < HD; c0 += 64) {
+    float acc[64];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) sm_acc[slot * 8 + e] = acc[e];
-  __syncthreads();
-  if (threadIdx.x < LPT) {
-    float M = -INFINITY;
-    for (int w = 0; w < 4; ++w)
-      for (int g = 0; g < TPW; ++g) M = fmaxf(M, sm_m[w * 32 + g * LPT + threadIdx.x]);
-    float L = 0.f, o[8];
+    for (int j = 0; j < 64; ++j) acc[j] = 0.f;
+    for (int t = lane; t < ctx; t += 32) {
+      const int page = bt[t / cache.page_tokens];
+      const uint4* vp = reinterpret_cast<const uint4*>(cache.base + kv_index(cache, layer, 1, page, h, t % cache.page_tokens) + c0);
+      uint4 vv[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) o[e] = 0.f;
-    for (int w = 0; w < 4; ++w)
-      for (int g = 0; g < TPW; ++g) {
-        const int sl = w * 32 + g * LPT + threadIdx.x;
-        const float mm = sm_m[sl];
-        if (mm == -INFINITY) continue;
-        const float f = expf(mm - M);
-        L += sm_l[sl] * f;
+      for (int c = 0; c < 8; ++c) vv[c] = ptx::ld_nc_u4(vp + c);
+      const float p = sc[t];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] += sm_acc[sl * 8 + e] * f;
+      for (int c = 0; c < 8; ++c) {
+        const float2 v0 = unpack_bf16x2(vv[c].x), v1 = unpack_bf16x2(vv[c].y), v2 = unpack_bf16x2(vv[c].z), v3 = unpack_bf16x2(vv[c].w);
+        acc[c * 8 + 0] = fmaf(p, v0.x, acc[c * 8 + 0]); acc[c * 8 + 1] = fmaf(p, v0.y, acc[c * 8 + 1]);
+        acc[c * 8 + 2] = fmaf(p, v1.x, acc[c * 8 + 2]); acc[c * 8 + 3] = fmaf(p, v1.y, acc[c * 8 + 3]);
+        acc[c * 8 + 4] = fmaf(p, v2.x, acc[c * 8 + 4]); acc[c * 8 + 5] = fmaf(p, v2.y, acc[c * 8 + 5]);
+        acc[c * 8 + 6] = fmaf(p, v3.x, acc[c * 8 + 6]); acc[c * 8 + 7] = fmaf(p, v3.y, acc[c * 8 + 7]);
       }
-    const float inv = 1.f / L;
-    uint4 pk;
-    pk.x = pack_bf16x2(o[0] * inv, o[1] * inv);
-    pk.y = pack_bf16x2(o[2] * inv, o[3] * inv);
-    pk.z = pack_bf16x2(o[4] * inv, o[5] * inv);
-    pk.w = pack_bf16x2(o[6] * inv, o[7] * inv);
-    *reinterpret_cast<uint4*>(out + static_cast<size_t>(b) * d + h * HD + threadIdx.x * 8) = pk;
+    }
+    // transpose-reduce over the 32 lanes: after the round with step s a lane keeps the half of the remaining
+    // dims selected by its bit s, so the survivors of lane l are dims 2l and 2l+1 of this chunk
+#pragma unroll
+    for (int step = 16, half = 32; step >= 1; step >>= 1, half >>= 1) {
+      const bool up = (lane & step) != 0;
+#pragma unroll
+      for (int j = 0; j < half; ++j) {
+        const float keep = up ? acc[j + half] : acc[j];
+        const float send = up ? acc[j] : acc[j + half];
+        acc[j] = keep + __shfl_xor_sync(0xffffffffu, send, step);
+      }
+    }
+    const int dim = c0 + 2 * lane;
+    const float2 vn = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(row + 2 * d + h * HD + dim));
+    const float o0 = (acc[0] + p_new * vn.x) * inv, o1 = (acc[1] + p_new * vn.y) * inv;
+    *reinterpret_cast<uint32_t*>(out + static_cast<size_t>(b) * d + h * HD + dim) = pack_bf16x2(o0, o1);
   }
 }
 
@@ -310,17 +305,33 @@ int attention_decode(const bf16* qkv, bf16* out, int B, int H, int hd, float sca
                      const int* block_table, const int* ctx_len, int rotary_dim, cudaStream_t s) {
   if (B <= 0) return 0;
   if (!cache) return (int)cudaErrorInvalidValue;
+  // per-warp shared memory: hd floats of q + one score per cached token
+  const int sc_cap = (cache->max_pages_per_row + 3) & ~3;  // max_pages_per_row == max_ctx >= any context length
+  const size_t smem = static_cast<size_t>(kDecodeWarps) * (hd + sc_cap) * sizeof(float);
+  if (smem > 200 * 1024) return (int)cudaErrorInvalidValue;
+  const int grid = (B * H + kDecodeWarps - 1) / kDecodeWarps;
+#define CCB_LAUNCH_DECODE(HDV)                                                                                      \
+  do {                                                                                                              \
+    static size_t configured = 0;                                                                                   \
+    if (smem > 48 * 1024 && smem > configured) {                                                                    \
+      cudaError_t e = cudaFuncSetAttribute(attention_decode_kernel<HDV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                           200 * 1024);                                                             \
+      if (e != cudaSuccess) return (int)e;                                                                          \
+      configured = 200 * 1024;                                                                                      \
+    }                                                                                                               \
+    cudaError_t le = launch_kernel(attention_decode_kernel<HDV>, dim3(grid), dim3(kDecodeWarps * 32), smem, s, true, \
+                                   qkv, out, B, H, scale, *cache, layer, block_table, ctx_len, rotary_dim, sc_cap);   \
+    if (le != cudaSuccess) return (int)le;                                                                          \
+  } while (0)
   if (hd == 64)
-    attention_decode_kernel<64><<<dim3(H, B), 128, 0, s>>>(qkv, out, H, scale, *cache, layer, block_table, ctx_len,
-                                                           rotary_dim);
+    CCB_LAUNCH_DECODE(64);
   else if (hd == 128)
-    attention_decode_kernel<128><<<dim3(H, B), 128, 0, s>>>(qkv, out, H, scale, *cache, layer, block_table, ctx_len,
-                                                            rotary_dim);
+    CCB_LAUNCH_DECODE(128);
   else if (hd == 256)
-    attention_decode_kernel<256><<<dim3(H, B), 128, 0, s>>>(qkv, out, H, scale, *cache, layer, block_table, ctx_len,
-                                                            rotary_dim);
+    CCB_LAUNCH_DECODE(256);
   else
     return (int)cudaErrorInvalidValue;
+#undef CCB_LAUNCH_DECODE
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
 }

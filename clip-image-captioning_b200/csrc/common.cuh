@@ -39,6 +39,9 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   }
 }
 
+// out-of-line copy for cold code (GEMM epilogues): one call instead of an inlined switch per element
+static __device__ __noinline__ float apply_act_call(float x, int act) { return apply_act(x, act); }
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

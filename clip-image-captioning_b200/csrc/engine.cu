@@ -219,6 +219,7 @@ int linear(ccb_ctx* c, const bf16* act, long long lda, int tokens, const Linear&
   g.out = out;
   g.ldo = ldo;
   g.out_bf16 = out_bf16;
+  g.allow_pdl = 1;
   return gemm_launch(g, c->gemm_ws, s);
 }
 
@@ -1008,6 +1009,15 @@ int ccb_op_linear(ccb_ctx* c, const void* x, int64_t lda, int tokens, const void
   g.force_bn = bn;
   g.force_split = split_k;
   RUN(gemm_launch(g, c->gemm_ws, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int ccb_debug_gemm_trace(ccb_ctx* c, void* trace_u64, int64_t stride_u64, int launches) {
+  if (!c) return -1;
+  c->gemm_ws.trace = static_cast<unsigned long long*>(trace_u64);
+  c->gemm_ws.trace_stride = stride_u64;
+  c->gemm_ws.trace_launches = launches > 0 ? launches : 1;
+  c->gemm_ws.trace_count = 0;
   return 0;
 }
 

@@ -54,9 +54,34 @@ int set_attr() {
 
 template <int BN>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, dim3 grid, cudaStream_t s) {
-  gemm_bf16_tn_kernel<BN><<<grid, GemmCfg<BN>::kThreads, GemmCfg<BN>::kSmemBytes, s>>>(ta, tb, p);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return fail("GEMM launch failed: %s", cudaGetErrorString(e));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(GemmCfg<BN>::kThreads);
+  cfg.dynamicSmemBytes = GemmCfg<BN>::kSmemBytes;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (p.split_k > 1) {
+    // the S splits of one output tile form one cluster and reduce over distributed shared memory
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 1;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = static_cast<unsigned>(p.split_k);
+    ++na;
+  }
+  if (p.pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_tn_kernel<BN>, ta, tb, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail("GEMM launch failed: %s", cudaGetErrorString(e));
+  }
   return 0;
 }
 
@@ -125,8 +150,8 @@ int gemm_launch(const GemmArgs& a, const GemmWorkspace& w, cudaStream_t stream) 
   p.rg_in = a.rg_in;
   p.rg_out = a.rg_out;
   p.rg_off = a.rg_off;
-  p.ws = w.ws;
-  p.sem = w.sem;
+  p.trace = w.trace ? w.trace + (w.trace_count++ % w.trace_launches) * w.trace_stride : nullptr;
+  p.pdl = (a.allow_pdl && pdl_enabled()) ? 1 : 0;
   // the vector store path assumes 16-byte aligned bases; fall back to scalar stores through odd ldo otherwise
   if (!swapped) {
     if ((reinterpret_cast<uintptr_t>(a.out) & 15) || (a.residual && (reinterpret_cast<uintptr_t>(a.residual) & 15)) ||
@@ -145,15 +170,11 @@ int gemm_launch(const GemmArgs& a, const GemmWorkspace& w, cudaStream_t stream) 
     split = w.num_sms / tiles;
     const int max_by_k = p.k_blocks / 4 > 0 ? p.k_blocks / 4 : 1;
     if (split > max_by_k) split = max_by_k;
-    if (split > 16) split = 16;
   }
   if (split > p.k_blocks) split = p.k_blocks;
-  if (split > 1) {
-    // every split must own at least one k-block: ceil(kb/split)*(split-1) < kb
-    while (split > 1 && ((p.k_blocks + split - 1) / split) * (split - 1) >= p.k_blocks) --split;
-    const size_t need = static_cast<size_t>(tiles) * split * bn * 128 * sizeof(float);
-    if (need > w.ws_bytes || tiles > w.sem_count) split = 1;
-  }
+  if (split > 8) split = 8;  // portable cluster size
+  // every split must own at least one k-block: ceil(kb/split)*(split-1) < kb
+  while (split > 1 && ((p.k_blocks + split - 1) / split) * (split - 1) >= p.k_blocks) --split;
   p.split_k = split;
   grid.z = split;
 

@@ -10,8 +10,11 @@
 //
 // One CTA computes one 128 x BN tile (optionally one K-split of it).  Warp roles: warp 0 = TMA producer,
 // warp 1 = TMEM allocator + MMA issuer (one elected lane), warps 2..5 = epilogue (one TMEM lane quadrant
-// each).  Split-K is deterministic: every split stores its raw fp32 tile to a workspace, the CTA that
-// arrives last on the tile's semaphore sums the splits in fixed order 0..S-1 and runs the epilogue.
+// each).  Split-K (used to fill the 148 SMs when there are few output tiles, i.e. in decode) runs the S splits of
+// one tile as ONE thread-block cluster (1,1,S): every CTA parks its fp32 accumulator in its own shared memory,
+// the cluster synchronises, and CTA z reduces the 8-column groups c with c % S == z by reading the S partial
+// tiles over distributed shared memory in the fixed order 0..S-1 (deterministic, no global workspace, no
+// atomics) before running the fused epilogue on them.
 #pragma once
 #include "common.cuh"
 #include "ptx.cuh"
@@ -21,7 +24,7 @@ namespace ccb {
 struct GemmParams {
   int Ra, Rb;        // valid rows of A / B (tile rows beyond are zero-filled by TMA and masked at the store)
   int k_blocks;      // K / 64
-  int split_k;       // >= 1
+  int split_k;       // >= 1; == cluster size along z
   // epilogue
   void* out;         // f32 or bf16
   int out_bf16;
@@ -33,48 +36,164 @@ struct GemmParams {
   int act;
   // normal-mode row remap: out_row = (i / rg_in) * rg_out + rg_off + (i % rg_in); rg_in == 0 -> identity
   int rg_in, rg_out, rg_off;
-  // split-K workspace and per-tile semaphores
-  float* ws;
-  int* sem;
+  // 1: launched with programmatic stream serialization inside the engine's chain: weight tiles are fetched
+  // before the dependency wait (they are never produced by the preceding kernel)
+  int pdl;
+  // optional timeline for tuning: 8 globaltimer stamps per CTA (null in production)
+  unsigned long long* trace;
 };
 
 template <int BN>
 struct GemmCfg {
   static constexpr int BM = 128;
   static constexpr int BK = 64;
-  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 5 : 6);
+  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 5 : 4);
+  static constexpr int kMinBlocks = 1;
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = BN < 32 ? 32 : BN;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  // Split-K staging (see the kernel): S slots x ceil(BN/8 / S) column groups x 8 columns x 128 rows of f32 per
+  // CTA, at most (BN/8 + 8) groups of 4 KB.  Decode tiles (BN <= 64) get their own region so that peers may push
+  // into it while this CTA's pipeline is still running (one cluster barrier); larger tiles reuse the pipeline
+  // stages after an extra barrier.
+  static constexpr bool kSeparateStaging = (BN <= 64);
+  static constexpr int kStagingBytes = (BN / 8 + 8) * 4096;
+  static_assert(kSeparateStaging || kStages * kStageBytes >= kStagingBytes, "staging must fit in the pipeline buffers");
+  static constexpr int kSmemBytes = kStages * kStageBytes + (kSeparateStaging ? kStagingBytes : 0) + 1024 /*align slack*/ +
+                                    256 /*barriers*/;
   static constexpr int kThreads = 192;
 };
 
+#define CCB_TRACE(slot)                                                                                   \
+  do {                                                                                                    \
+    if (p.trace != nullptr && lane == 0)                                                                  \
+      p.trace[((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8ull + (slot)] = ptx::globaltimer_ns(); \
+  } while (0)
+
+// Fused epilogue on CW accumulator columns [c0, c0 + CW) of this thread's row.  Kept small on purpose: it runs
+// once per tile, so its instructions are cold in the instruction cache (a fully unrolled epilogue with the
+// activation switch inlined was 22 K instructions and cost ~15 us per tile in instruction fetches).
+template <int CW>
+__device__ __forceinline__ void gemm_epilogue_cols(const GemmParams& p, float (&acc)[CW], int i, bool i_ok,
+                                                   long long out_row, float bias_i, int j0, bool vec_ok) {
+  if (!i_ok) return;
+  if (p.transposed) {
+#pragma unroll
+    for (int v = 0; v < CW; ++v) acc[v] += bias_i;
+  } else if (p.bias != nullptr) {
+#pragma unroll
+    for (int v = 0; v < CW; ++v) acc[v] += (j0 + v < p.Rb) ? __ldg(p.bias + j0 + v) : 0.f;
+  }
+  if (p.act == ACT_RELU) {
+#pragma unroll
+    for (int v = 0; v < CW; ++v) acc[v] = fmaxf(acc[v], 0.f);
+  } else if (p.act == ACT_GELU_NEW) {
+    // 0.5 x (1 + tanh(u)) == x - x / (1 + exp(2u)); exp2-based __expf + fast divide: ~1e-6 relative error, far
+    // below the bf16 rounding of the stored value, and a handful of instructions (the epilogue has 4 warps)
+#pragma unroll
+    for (int v = 0; v < CW; ++v) {
+      const float x = acc[v];
+      const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+      acc[v] = x - __fdividef(x, 1.f + __expf(2.f * u));
+    }
+  } else if (p.act == ACT_QUICKGELU) {
+#pragma unroll
+    for (int v = 0; v < CW; ++v) acc[v] = __fdividef(acc[v], 1.f + __expf(-1.702f * acc[v]));
+  } else if (p.act != ACT_NONE) {
+#pragma unroll
+    for (int v = 0; v < CW; ++v) acc[v] = apply_act_call(acc[v], p.act);  // static indices keep acc in registers
+  }
+  if (p.transposed) {
+    // lanes hold consecutive features i -> coalesced accesses for every token j.  All residual loads are issued
+    // before the first store: out may alias residual (in-place residual stream), so a load placed after a store
+    // could not be hoisted by the compiler and the CW load latencies would serialise.
+    if (p.residual) {
+      float res[CW];
+#pragma unroll
+      for (int v = 0; v < CW; ++v) res[v] = (j0 + v < p.Rb) ? p.residual[static_cast<long long>(j0 + v) * p.ldr + i] : 0.f;
+#pragma unroll
+      for (int v = 0; v < CW; ++v) acc[v] += res[v];
+    }
+#pragma unroll
+    for (int v = 0; v < CW; ++v) {
+      const int j = j0 + v;
+      if (j < p.Rb) {
+        if (p.out_bf16)
+          reinterpret_cast<__nv_bfloat16*>(p.out)[static_cast<long long>(j) * p.ldo + i] = __float2bfloat16_rn(acc[v]);
+        else
+          reinterpret_cast<float*>(p.out)[static_cast<long long>(j) * p.ldo + i] = acc[v];
+      }
+    }
+  } else if (vec_ok && j0 + CW <= p.Rb) {
+    if (p.residual) {
+#pragma unroll
+      for (int v = 0; v < CW; v += 4) {
+        const float4 r4 = *reinterpret_cast<const float4*>(p.residual + out_row * p.ldr + j0 + v);
+        acc[v] += r4.x; acc[v + 1] += r4.y; acc[v + 2] += r4.z; acc[v + 3] += r4.w;
+      }
+    }
+    if (p.out_bf16) {
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + out_row * p.ldo + j0;
+#pragma unroll
+      for (int v = 0; v < CW; v += 8) {
+        uint4 pk;
+        pk.x = pack_bf16x2(acc[v], acc[v + 1]);
+        pk.y = pack_bf16x2(acc[v + 2], acc[v + 3]);
+        pk.z = pack_bf16x2(acc[v + 4], acc[v + 5]);
+        pk.w = pack_bf16x2(acc[v + 6], acc[v + 7]);
+        *reinterpret_cast<uint4*>(o + v) = pk;
+      }
+    } else {
+      float* o = reinterpret_cast<float*>(p.out) + out_row * p.ldo + j0;
+#pragma unroll
+      for (int v = 0; v < CW; v += 4)
+        *reinterpret_cast<float4*>(o + v) = make_float4(acc[v], acc[v + 1], acc[v + 2], acc[v + 3]);
+    }
+  } else {
+    if (p.residual) {
+      float res[CW];
+#pragma unroll
+      for (int v = 0; v < CW; ++v) res[v] = (j0 + v < p.Rb) ? p.residual[out_row * p.ldr + j0 + v] : 0.f;
+#pragma unroll
+      for (int v = 0; v < CW; ++v) acc[v] += res[v];
+    }
+#pragma unroll
+    for (int v = 0; v < CW; ++v) {
+      const int j = j0 + v;
+      if (j < p.Rb) {
+        if (p.out_bf16)
+          reinterpret_cast<__nv_bfloat16*>(p.out)[out_row * p.ldo + j] = __float2bfloat16_rn(acc[v]);
+        else
+          reinterpret_cast<float*>(p.out)[out_row * p.ldo + j] = acc[v];
+      }
+    }
+  }
+}
+
 template <int BN>
-__global__ void __launch_bounds__(192, 1) gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
+__global__ void __launch_bounds__(192, GemmCfg<BN>::kMinBlocks) gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tma_a,
                                                            const __grid_constant__ CUtensorMap tma_b,
                                                            const GemmParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + kStages * Cfg::kStageBytes;
-  // barrier layout: full[kStages], empty[kStages], tmem_full, then the TMEM address slot and a flag word
+  constexpr uint32_t kDataBytes = kStages * Cfg::kStageBytes + (Cfg::kSeparateStaging ? Cfg::kStagingBytes : 0);
+  const uint32_t bar_base = smem_base + kDataBytes;
+  // barrier layout: full[kStages], empty[kStages], tmem_full, then the TMEM address slot
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
   const uint32_t tmem_full_bar = bar_base + 8u * (2 * kStages);
   const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 1);
-  const uint32_t flag_slot = tmem_slot + 4;
   uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + kStages * Cfg::kStageBytes + 8 * (2 * kStages + 1));
-  volatile uint32_t* flag_ptr = tmem_slot_ptr + 1;
-  (void)flag_slot;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + kDataBytes + 8 * (2 * kStages + 1));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (warp == 0) CCB_TRACE(0);  // entry
 
-  // K range of this split
+  // K range of this split (blockIdx.z == rank in the cluster)
   const int kb_per = (p.k_blocks + p.split_k - 1) / p.split_k;
   const int kb_begin = blockIdx.z * kb_per;
   int kb_end = kb_begin + kb_per;
@@ -98,9 +217,17 @@ __global__ void __launch_bounds__(192, 1) gemm_bf16_tn_kernel(const __grid_const
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  if (warp == 0) CCB_TRACE(1);  // setup done
+  ptx::grid_dep_launch();       // the next kernel of the stream may start its prologue now
+  if (p.split_k > 1) ptx::cluster_arrive();  // "this CTA is running": completed by the wait ahead of the pushes
 
   const int row_a0 = blockIdx.x * Cfg::BM;
   const int row_b0 = blockIdx.y * BN;
+  const int quad = warp & 3;  // TMEM lane quadrant an epilogue warp may access
+  const int i = row_a0 + quad * 32 + lane;
+  const bool i_ok = i < p.Ra;
+  const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+  const uint32_t red_base = smem_base + (Cfg::kSeparateStaging ? kStages * Cfg::kStageBytes : 0);  // split-K staging
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -108,18 +235,36 @@ __global__ void __launch_bounds__(192, 1) gemm_bf16_tn_kernel(const __grid_const
       // weights are streamed once (evict-first); activations are re-read by many CTAs (evict-last)
       const uint64_t hint_a = p.transposed ? ptx::kEvictFirst : ptx::kEvictLast;
       const uint64_t hint_b = p.transposed ? ptx::kEvictLast : ptx::kEvictNormal;
-      for (int it = 0; it < nkb; ++it) {
+      // Weights (A when transposed, else B) do not depend on the preceding kernel: with PDL their first
+      // kStages tiles are requested before the dependency wait, the activation tiles right after it.
+      const CUtensorMap* w_map = p.transposed ? &tma_a : &tma_b;
+      const CUtensorMap* x_map = p.transposed ? &tma_b : &tma_a;
+      const uint32_t w_off = p.transposed ? 0u : static_cast<uint32_t>(Cfg::kABytes);
+      const uint32_t x_off = p.transposed ? static_cast<uint32_t>(Cfg::kABytes) : 0u;
+      const int w_row = p.transposed ? row_a0 : row_b0;
+      const int x_row = p.transposed ? row_b0 : row_a0;
+      const uint64_t w_hint = p.transposed ? hint_a : hint_b;
+      const uint64_t x_hint = p.transposed ? hint_b : hint_a;
+      const int pre = p.pdl ? (nkb < kStages ? nkb : kStages) : 0;
+      for (int it = 0; it < pre; ++it) {
+        ptx::mbar_arrive_expect_tx(full_bar(it), Cfg::kStageBytes);
+        ptx::tma_load_2d(smem_base + it * Cfg::kStageBytes + w_off, w_map, full_bar(it), (kb_begin + it) * Cfg::BK, w_row, w_hint);
+      }
+      ptx::grid_dep_wait();
+      for (int it = 0; it < pre; ++it)
+        ptx::tma_load_2d(smem_base + it * Cfg::kStageBytes + x_off, x_map, full_bar(it), (kb_begin + it) * Cfg::BK, x_row, x_hint);
+      for (int it = pre; it < nkb; ++it) {
         const int s = it % kStages;
         const uint32_t ph = (it / kStages) & 1;
         ptx::mbar_wait(empty_bar(s), ph ^ 1);
-        const uint32_t sa = smem_base + s * Cfg::kStageBytes;
-        const uint32_t sb = sa + Cfg::kABytes;
+        const uint32_t st = smem_base + s * Cfg::kStageBytes;
         ptx::mbar_arrive_expect_tx(full_bar(s), Cfg::kStageBytes);
         const int kcoord = (kb_begin + it) * Cfg::BK;
-        ptx::tma_load_2d(sa, &tma_a, full_bar(s), kcoord, row_a0, hint_a);
-        ptx::tma_load_2d(sb, &tma_b, full_bar(s), kcoord, row_b0, hint_b);
+        ptx::tma_load_2d(st + w_off, w_map, full_bar(s), kcoord, w_row, w_hint);
+        ptx::tma_load_2d(st + x_off, x_map, full_bar(s), kcoord, x_row, x_hint);
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0) {
@@ -129,6 +274,7 @@ __global__ void __launch_bounds__(192, 1) gemm_bf16_tn_kernel(const __grid_const
         const uint32_t ph = (it / kStages) & 1;
         ptx::mbar_wait(full_bar(s), ph);
         ptx::tc_fence_after();
+        if (it == 0) CCB_TRACE(2);  // first stage landed
         const uint32_t sa = smem_base + s * Cfg::kStageBytes;
         const uint32_t sb = sa + Cfg::kABytes;
         const uint64_t adesc = ptx::umma_desc_k_sw128(sa);
@@ -141,158 +287,112 @@ __global__ void __launch_bounds__(192, 1) gemm_bf16_tn_kernel(const __grid_const
         ptx::umma_commit(empty_bar(s));  // frees the smem stage when these MMAs retire
       }
       ptx::umma_commit(tmem_full_bar);   // accumulator complete
+      CCB_TRACE(3);                      // all MMAs issued
     }
+    __syncwarp();
   } else {
-    // ------------------------------------------------------------ epilogue (warps 2..5)
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
-    const int i = row_a0 + quad * 32 + lane;
-    const bool i_ok = i < p.Ra;
+    // ------------------------------------------------------------ epilogue warps 2..5: accumulator is ready
+    ptx::grid_dep_wait();  // (returns at once unless this is a PDL launch) before any global read / write below
     ptx::mbar_wait(tmem_full_bar, 0);
     ptx::tc_fence_after();
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    if (warp == 2) CCB_TRACE(4);  // accumulator ready
+  }
 
-    bool do_epilogue = true;
-    const int tile_id = blockIdx.y * gridDim.x + blockIdx.x;
-    float* ws_tile = nullptr;
-    if (p.split_k > 1) {
-      ws_tile = p.ws + static_cast<size_t>(tile_id) * p.split_k * (BN * 128);
-      float* mine = ws_tile + static_cast<size_t>(blockIdx.z) * (BN * 128) + quad * 32 + lane;
+  long long out_row = i;
+  if (!p.transposed && p.rg_in > 0) out_row = static_cast<long long>(i / p.rg_in) * p.rg_out + p.rg_off + (i % p.rg_in);
+  const bool vec_ok = !p.transposed && ((p.ldo & 7) == 0) && (p.residual == nullptr || (p.ldr & 3) == 0);
+
+  if (p.split_k > 1) {
+    // ------------------------------------------------------------ split-K: push-based cluster reduction
+    // The BN/8 groups of 8 columns are dealt round-robin to the S CTAs of the cluster (owner of group c = c % S).
+    // Every CTA PUSHES its partial of group c into slot [its rank] of the owner's staging area with fire-and-forget
+    // remote stores (no load round trips over the cluster network); after one cluster barrier each owner sums
+    // its slots in the fixed order 0..S-1 (deterministic) out of its OWN shared memory and runs the epilogue.
+    const uint32_t S = p.split_k;
+    const uint32_t my_rank = blockIdx.z;
+    const uint32_t NC = BN / 8;
+    const uint32_t MPO = (NC + S - 1) / S;  // groups per owner (upper bound)
+    ptx::cluster_wait();          // every CTA of the cluster has started: its shared memory may be written
+    if (!Cfg::kSeparateStaging) {
+      // the staging area aliases the pipeline stages: peers may only write once every CTA's MMAs have retired
+      ptx::cluster_arrive();
+      ptx::cluster_wait();
+    }
+    if (warp >= 2) {
+      const uint32_t row_off = static_cast<uint32_t>(quad * 32 + lane) * 4u;
+#pragma unroll 1
+      for (uint32_t c = 0; c < NC; ++c) {
+        uint32_t r[8];
+        ptx::tmem_ld8(taddr + c * 8, r);
+        ptx::tmem_ld_wait();
+        const uint32_t local = red_base + ((my_rank * MPO + c / S) * 8u) * 512u + row_off;
+        const uint32_t remote = ptx::mapa_shared(local, c % S);
+#pragma unroll
+        for (int v = 0; v < 8; ++v) ptx::st_dsmem_f32(remote + v * 512u, __uint_as_float(r[v]));
+      }
+    }
+    ptx::cluster_arrive();        // release: the pushes above are visible to the owners after the wait
+    ptx::cluster_wait();
+    if (warp == 2) CCB_TRACE(5);
+    if (warp >= 2) {
+      const float bias_i = (p.transposed && p.bias != nullptr && i_ok) ? p.bias[i] : 0.f;
+      const uint32_t row_off = static_cast<uint32_t>(quad * 32 + lane) * 4u;
+#pragma unroll 1
+      for (uint32_t c = my_rank, li = 0; c < NC; c += S, ++li) {
+        const int j0 = row_b0 + static_cast<int>(c) * 8;
+        if (j0 >= p.Rb) break;
+        float acc[8];
+#pragma unroll
+        for (int v = 0; v < 8; ++v) acc[v] = 0.f;
+#pragma unroll 1
+        for (uint32_t sl = 0; sl < S; ++sl) {        // fixed order 0..S-1: deterministic sum
+          const uint32_t src = red_base + ((sl * MPO + li) * 8u) * 512u + row_off;
+#pragma unroll
+          for (int v = 0; v < 8; ++v) acc[v] += ptx::ld_shared_f32(src + v * 512u);
+        }
+        gemm_epilogue_cols<8>(p, acc, i, i_ok, out_row, bias_i, j0, vec_ok);
+      }
+      if (warp == 2) CCB_TRACE(6);  // epilogue done
+    }
+  } else if (warp >= 2) {
+    const float bias_i = (p.transposed && p.bias != nullptr && i_ok) ? p.bias[i] : 0.f;
+    if (p.transposed) {
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 8) {
+        const int j0 = row_b0 + c0;
+        if (j0 >= p.Rb) break;
+        uint32_t r[8];
+        ptx::tmem_ld8(taddr + c0, r);
+        ptx::tmem_ld_wait();
+        float acc[8];
+#pragma unroll
+        for (int v = 0; v < 8; ++v) acc[v] = __uint_as_float(r[v]);
+        gemm_epilogue_cols<8>(p, acc, i, i_ok, out_row, bias_i, j0, vec_ok);
+      }
+    } else {
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
+        const int j0 = row_b0 + c0;
+        if (j0 >= p.Rb) break;
         uint32_t r[32];
         ptx::tmem_ld32(taddr + c0, r);
         ptx::tmem_ld_wait();
-#pragma unroll
-        for (int v = 0; v < 32; ++v) mine[(c0 + v) * 128] = __uint_as_float(r[v]);
-      }
-      __threadfence();
-      ptx::named_bar_sync(1, 128);
-      if (warp == 2 && lane == 0) {
-        const int prev = atomicAdd(p.sem + tile_id, 1);
-        const int last = (prev == p.split_k - 1);
-        if (last) p.sem[tile_id] = 0;  // self-reset for the next launch
-        *flag_ptr = last;
-      }
-      ptx::named_bar_sync(1, 128);
-      do_epilogue = (*flag_ptr != 0);
-      if (do_epilogue) __threadfence();
-    }
-
-    if (do_epilogue) {
-      long long out_row = i;
-      if (!p.transposed && p.rg_in > 0) out_row = static_cast<long long>(i / p.rg_in) * p.rg_out + p.rg_off + (i % p.rg_in);
-      const float bias_i = (p.transposed && p.bias != nullptr && i_ok) ? p.bias[i] : 0.f;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
         float acc[32];
-        if (p.split_k > 1) {
 #pragma unroll
-          for (int v = 0; v < 32; ++v) acc[v] = 0.f;
-          // fixed summation order 0..S-1 (deterministic); loads of 4 splits are in flight together
-          for (int s0 = 0; s0 < p.split_k; s0 += 4) {
-            float t[4][32];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              if (s0 + u < p.split_k) {
-                const float* src = ws_tile + static_cast<size_t>(s0 + u) * (BN * 128) + quad * 32 + lane;
-#pragma unroll
-                for (int v = 0; v < 32; ++v) t[u][v] = ptx::ldcg_f32(src + (c0 + v) * 128);
-              }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              if (s0 + u < p.split_k) {
-#pragma unroll
-                for (int v = 0; v < 32; ++v) acc[v] += t[u][v];
-              }
-            }
-          }
-        } else {
-          uint32_t r[32];
-          ptx::tmem_ld32(taddr + c0, r);
-          ptx::tmem_ld_wait();
-#pragma unroll
-          for (int v = 0; v < 32; ++v) acc[v] = __uint_as_float(r[v]);
-        }
-        const int j0 = row_b0 + c0;
-        if (j0 >= p.Rb) break;
-        if (p.transposed) {
-          // lanes hold consecutive features i -> coalesced stores for every token j
-#pragma unroll
-          for (int v = 0; v < 32; ++v) {
-            const int j = j0 + v;
-            if (i_ok && j < p.Rb) {
-              float x = acc[v] + bias_i;
-              x = apply_act(x, p.act);
-              if (p.residual) x += p.residual[static_cast<long long>(j) * p.ldr + i];
-              if (p.out_bf16)
-                reinterpret_cast<__nv_bfloat16*>(p.out)[static_cast<long long>(j) * p.ldo + i] = __float2bfloat16_rn(x);
-              else
-                reinterpret_cast<float*>(p.out)[static_cast<long long>(j) * p.ldo + i] = x;
-            }
-          }
-        } else if (i_ok) {
-          const bool full = (j0 + 32 <= p.Rb);
-          const bool vec_ok = full && ((p.ldo & 7) == 0) && (p.residual == nullptr || (p.ldr & 3) == 0);
-          if (vec_ok) {
-#pragma unroll
-            for (int v = 0; v < 32; v += 4) {
-              float x[4] = {acc[v], acc[v + 1], acc[v + 2], acc[v + 3]};
-              if (p.bias) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + j0 + v));
-                x[0] += b4.x; x[1] += b4.y; x[2] += b4.z; x[3] += b4.w;
-              }
-#pragma unroll
-              for (int q = 0; q < 4; ++q) x[q] = apply_act(x[q], p.act);
-              if (p.residual) {
-                const float4 r4 = *reinterpret_cast<const float4*>(p.residual + out_row * p.ldr + j0 + v);
-                x[0] += r4.x; x[1] += r4.y; x[2] += r4.z; x[3] += r4.w;
-              }
-              acc[v] = x[0]; acc[v + 1] = x[1]; acc[v + 2] = x[2]; acc[v + 3] = x[3];
-            }
-            if (p.out_bf16) {
-              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + out_row * p.ldo + j0;
-#pragma unroll
-              for (int v = 0; v < 32; v += 8) {
-                uint4 pk;
-                pk.x = pack_bf16x2(acc[v], acc[v + 1]);
-                pk.y = pack_bf16x2(acc[v + 2], acc[v + 3]);
-                pk.z = pack_bf16x2(acc[v + 4], acc[v + 5]);
-                pk.w = pack_bf16x2(acc[v + 6], acc[v + 7]);
-                *reinterpret_cast<uint4*>(o + v) = pk;
-              }
-            } else {
-              float* o = reinterpret_cast<float*>(p.out) + out_row * p.ldo + j0;
-#pragma unroll
-              for (int v = 0; v < 32; v += 4)
-                *reinterpret_cast<float4*>(o + v) = make_float4(acc[v], acc[v + 1], acc[v + 2], acc[v + 3]);
-            }
-          } else {
-#pragma unroll
-            for (int v = 0; v < 32; ++v) {
-              const int j = j0 + v;
-              if (j < p.Rb) {
-                float x = acc[v] + (p.bias ? p.bias[j] : 0.f);
-                x = apply_act(x, p.act);
-                if (p.residual) x += p.residual[out_row * p.ldr + j];
-                if (p.out_bf16)
-                  reinterpret_cast<__nv_bfloat16*>(p.out)[out_row * p.ldo + j] = __float2bfloat16_rn(x);
-                else
-                  reinterpret_cast<float*>(p.out)[out_row * p.ldo + j] = x;
-              }
-            }
-          }
-        }
+        for (int v = 0; v < 32; ++v) acc[v] = __uint_as_float(r[v]);
+        gemm_epilogue_cols<32>(p, acc, i, i_ok, out_row, bias_i, j0, vec_ok);
       }
     }
-    ptx::tc_fence_before();
+    if (warp == 2) CCB_TRACE(6);  // epilogue done
   }
 
+  ptx::tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
+  if (warp == 0) CCB_TRACE(7);  // exit
 }
 
 }  // namespace ccb

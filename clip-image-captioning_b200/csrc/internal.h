@@ -10,6 +10,29 @@ namespace ccb {
 
 typedef __nv_bfloat16 bf16;
 
+// Programmatic dependent launch for the kernels of the decode chain (they all call ptx::grid_dep_wait() before
+// touching activations): CCB_PDL=0 in the environment switches it off.
+bool pdl_enabled();
+
+// <<<>>> with optional launch attributes (PDL).  Returns the launch status.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl,
+                                 Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  if (pdl && pdl_enabled()) {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ------------------------------------------------------------------ GEMM (gemm.cu)
 struct GemmWorkspace {
   float* ws = nullptr;      // split-K partial tiles
@@ -17,6 +40,11 @@ struct GemmWorkspace {
   int* sem = nullptr;       // per-tile semaphores (zero-initialised, self-resetting)
   int sem_count = 0;
   int num_sms = 148;
+  // tuning only: per-CTA timelines; launch n writes to trace + (n % trace_launches) * trace_stride
+  unsigned long long* trace = nullptr;
+  long long trace_stride = 0;
+  int trace_launches = 1;
+  mutable long long trace_count = 0;
 };
 
 struct GemmArgs {
@@ -37,6 +65,8 @@ struct GemmArgs {
   int force_orientation = 0;     // 0 auto, 1 normal, 2 swapped
   int force_bn = 0;              // 0 auto
   int force_split = 0;           // 0 auto
+  int allow_pdl = 0;             // 1: launched inside the engine's own chain (weights are never produced by the
+                                 // preceding kernel, so their loads may start before the dependency wait)
 };
 
 int gemm_init(int device);  // resolves cuTensorMapEncodeTiled, sets smem attributes

@@ -1,7 +1,10 @@
 // Row-wise and glue kernels: LayerNorm, ViT patchify / token assembly, mapper constant rows, embedding
 // gathers.  All are HBM/L2-bound streaming kernels: 16-byte vector accesses, one CTA per row.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "internal.h"
+#include "ptx.cuh"
 
 namespace ccb {
 
@@ -22,6 +25,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         OutT* __restrict__ y, long long ldy, int d) {
   extern __shared__ float row[];
   __shared__ float scratch[32];
+  ptx::grid_dep_wait();
+  ptx::grid_dep_launch();
   const float* xr = x + static_cast<long long>(blockIdx.x) * ldx;
   float s = 0.f;
   for (int c = threadIdx.x * 4; c < d; c += blockDim.x * 4) {
@@ -188,6 +193,8 @@ __global__ void __launch_bounds__(256) cast_kernel(const float* __restrict__ x, 
 __global__ void __launch_bounds__(256) embed_kernel(const bf16* __restrict__ wte, const bf16* __restrict__ wpe,
                                                     const int* __restrict__ tokens, const int* __restrict__ positions,
                                                     float* __restrict__ h, int d) {
+  ptx::grid_dep_wait();
+  ptx::grid_dep_launch();
   const int r = blockIdx.x;
   const int tok = tokens[r];
   const uint2* te = reinterpret_cast<const uint2*>(wte + static_cast<long long>(tok) * d);
@@ -285,8 +292,10 @@ int layernorm_f32_bf16(const float* x, long long ldx, const float* gamma, const 
                        long long ldy, int rows, int d, cudaStream_t s) {
   if (rows <= 0) return 0;
   if (d % 4 || ldx % 4 || ldy % 4) return (int)cudaErrorInvalidValue;
-  layernorm_kernel<bf16><<<rows, 256, d * sizeof(float), s>>>(x, ldx, gamma, beta, eps, y, ldy, d);
-  CCB_LAUNCH_CHECK();
+  {
+    cudaError_t e = launch_kernel(layernorm_kernel<bf16>, dim3(rows), dim3(256), d * sizeof(float), s, true, x, ldx, gamma, beta, eps, y, ldy, d);
+    if (e != cudaSuccess) return (int)e;
+  }
   return 0;
 }
 int layernorm_f32_f32(const float* x, long long ldx, const float* gamma, const float* beta, float eps, float* y,
@@ -346,8 +355,10 @@ int embed_tokens(const bf16* wte, const bf16* wpe, const int* tokens, const int*
                  cudaStream_t s) {
   if (rows <= 0) return 0;
   if (d % 4) return (int)cudaErrorInvalidValue;
-  embed_kernel<<<rows, 256, 0, s>>>(wte, wpe, tokens, positions, h, d);
-  CCB_LAUNCH_CHECK();
+  {
+    cudaError_t e = launch_kernel(embed_kernel, dim3(rows), dim3(256), 0, s, true, wte, wpe, tokens, positions, h, d);
+    if (e != cudaSuccess) return (int)e;
+  }
   return 0;
 }
 
@@ -366,6 +377,14 @@ int gather_rows_f32(const float* src, long long lds, int gi, int go, int off, fl
   gather_rows_kernel<<<rows, 256, 0, s>>>(src, lds, gi, go, off, dst, ldd, d);
   CCB_LAUNCH_CHECK();
   return 0;
+}
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("CCB_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
 }
 
 }  // namespace ccb

@@ -12,6 +12,7 @@
 
 #include "common.cuh"
 #include "internal.h"
+#include "ptx.cuh"
 
 namespace ccb {
 
@@ -113,6 +114,8 @@ __device__ __forceinline__ int block_sum_i(int v, int* scratch) {
 __global__ void __launch_bounds__(kSampThreads) greedy_kernel(const float* __restrict__ logits, long long ld, int V,
                                                               int* __restrict__ next) {
   __shared__ ArgMax scratch[32];
+  ptx::grid_dep_wait();
+  ptx::grid_dep_launch();
   const float* row = logits + static_cast<long long>(blockIdx.x) * ld;
   ArgMax a;
   a.v = -INFINITY;
@@ -621,6 +624,8 @@ __global__ void __launch_bounds__(kSampThreads) beam_step_kernel(const BeamArgs 
 __global__ void advance_kernel(const int* __restrict__ next, int rows, int* tokens_out, int max_len, int* lengths,
                                int* stops, uint8_t* finished, int* ctx_len, int* step, int stop_token, int max_stops,
                                int eos_token) {
+  ptx::grid_dep_wait();
+  ptx::grid_dep_launch();
   const int st = *step;
   for (int r = threadIdx.x; r < rows; r += blockDim.x) {
     const int tok = next[r];
@@ -643,8 +648,7 @@ __global__ void advance_kernel(const int* __restrict__ next, int rows, int* toke
 
 int sample_greedy(const float* logits, long long ld, int B, int V, int* next, cudaStream_t s) {
   if (B <= 0) return 0;
-  greedy_kernel<<<B, kSampThreads, 0, s>>>(logits, ld, V, next);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_kernel(greedy_kernel, dim3(B), dim3(kSampThreads), 0, s, true, logits, ld, V, next);
   return e == cudaSuccess ? 0 : (int)e;
 }
 
@@ -711,9 +715,8 @@ int increment_rows(int* x, int rows, int* scalar, cudaStream_t s) {
 
 int advance_rows(const int* next, int rows, int* tokens_out, int max_len, int* lengths, int* stops, uint8_t* finished,
                  int* ctx_len, int* step, int stop_token, int max_stops, int eos_token, cudaStream_t s) {
-  advance_kernel<<<1, 1024, 0, s>>>(next, rows, tokens_out, max_len, lengths, stops, finished, ctx_len, step,
-                                    stop_token, max_stops, eos_token);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_kernel(advance_kernel, dim3(1), dim3(1024), 0, s, true, next, rows, tokens_out, max_len, lengths,
+                                stops, finished, ctx_len, step, stop_token, max_stops, eos_token);
   return e == cudaSuccess ? 0 : (int)e;
 }
 

@@ -152,6 +152,10 @@ CCB_API int ccb_beam_step(ccb_ctx* ctx, const float* logits, int64_t ld, int N, 
 CCB_API int ccb_op_linear(ccb_ctx* ctx, const void* x, int64_t lda, int tokens, const void* w, int features, int K,
                   const float* bias, int act, const float* residual, int64_t ldr, void* out, int64_t ldo,
                   int out_bf16, int orientation, int bn, int split_k, void* stream);
+/* tuning aid: when non-NULL, GEMM launch n of this context writes 8 globaltimer stamps per CTA to
+ * trace[(n % launches) * stride_u64 + cta * 8 + k] (entry, setup, first tile landed, MMAs issued, accumulator ready,
+ * cluster reduction reached, epilogue done, exit).  NULL (the default) disables it. */
+CCB_API int ccb_debug_gemm_trace(ccb_ctx* ctx, void* trace_u64, int64_t stride_u64, int launches);
 /* y = LayerNorm(x) over the last dim: x f32 [rows, d] -> y bf16 [rows, d] */
 CCB_API int ccb_op_layernorm(ccb_ctx* ctx, const float* x, const float* gamma, const float* beta, float eps, void* y_bf16,
                      int rows, int d, void* stream);
