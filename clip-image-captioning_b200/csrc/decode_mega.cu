@@ -1,0 +1,932 @@
+// Persistent decode-step kernel for GPT-2 style models (lms/GPT2.py:17-19 -> HF GPT2LMHeadModel, one new token per
+// row against the KV cache): embed -> L x [ln_1, c_attn, attention, c_proj, ln_2, c_fc, gelu_new, mlp.c_proj] -> ln_f
+// in ONE cooperative launch of one CTA per SM.
+//
+// Why: a decode step is bound by streaming every weight once from HBM (3.1 GB for GPT2-XL) but consists of ~340
+// dependent little operators; as separate kernels each of them pays launch, prologue, pipeline ramp and tail.  Here
+// the weight stream never stops:
+//   warp 0  W producer : walks this CTA's share of ALL weight tiles of ALL layers in consumption order and keeps a
+//                        deep TMA ring (128 rows x 64 k, 16 KB per stage) full.  It depends on nothing but free ring
+//                        slots, so it runs ahead of the math across operator and layer boundaries.
+//   warp 1  X producer : TMA-loads the activation tile (all rows x 64 k) each unit needs, after the grid-wide phase
+//                        counter says the producing phase is complete.
+//   warp 2  MMA issuer : tcgen05.mma 128 x N x 16 (weights on the 128-row side, rows = N <= 256), fp32 accumulator
+//                        in TMEM, double buffered.
+//   warp 3             : TMEM allocation.
+//   warps 4-11 compute : GEMM epilogue (TMEM -> fp32 split-K partials in an L2-resident workspace) and the vector
+//                        phases between the GEMMs, which fold the partials: residual + bias + LayerNorm, attention
+//                        over the paged KV cache (+ append of the new K/V), bias + gelu_new.
+// Work split: stream-K (mega.h).  Phases are separated by a grid barrier (one monotonically increasing counter in
+// global memory, red.release / ld.acquire); cross-CTA data is read with ld.global.cg or TMA (after a proxy fence).
+//
+// Everything in here runs on a handful of warps per SM with nothing to hide latency behind, so the loops are written
+// for a short dependent-instruction chain: no integer division or 64-bit index arithmetic inside loops, ring stage /
+// phase kept incrementally, phases as out-of-line functions (the kernel must stay resident in the instruction cache).
+#include <cuda.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "mega.h"
+#include "ptx.cuh"
+
+namespace ccb {
+
+namespace {
+
+constexpr int kThreads = 384;
+constexpr int kComputeThreads = 256;
+constexpr int kComputeWarp0 = 4;
+constexpr int kWStage = 128 * 64 * 2;
+constexpr int kTblMax = 512;
+constexpr int kVecScratch = 64 * 1024;   // vector-phase scratch = the (idle) X ring: 8 KB per compute warp
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ float4 ldcg_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float2 ldcg_f2(const float* p) {
+  float2 v;
+  asm volatile("ld.global.cg.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// 16-byte asynchronous copy global -> shared; src_bytes == 0 writes zeros
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+
+// wait until the phase counter reaches `target` (bounded: a protocol bug traps instead of hanging the GPU)
+__device__ __forceinline__ void poll_counter(const unsigned* ctr, unsigned target) {
+  if (ld_acquire_u32(ctr) >= target) return;
+  const uint64_t t0 = ptx::globaltimer_ns();
+  uint32_t spins = 0;
+  while (ld_acquire_u32(ctr) < target) {
+    if ((++spins & 0x3ff) == 0 && ptx::globaltimer_ns() - t0 > 4000000000ull) __trap();
+  }
+}
+
+// fine-grained role stamps of layer 1 (tuning only): slot k of CTA c at trace[ncta * 2 * (8L + 2) + c * 64 + k]
+#define MEGA_RSTAMP(layer, slot)                                                                         \
+  do {                                                                                                   \
+    if (p.trace != nullptr && (layer) == 1)                                                              \
+      p.trace[static_cast<size_t>(p.ncta) * (2 * (8 * p.L + 2)) + static_cast<size_t>(blockIdx.x) * 64 + (slot)] = ptx::globaltimer_ns(); \
+  } while (0)
+
+// This CTA's share of one GEMM kind (the same in every layer): n units starting at (tile0, kb0), row-tile major.
+struct KindSched {
+  int n, tile0, kb0, kb;
+};
+
+struct ComputeCtx {
+  int ct, cw, lane;      // thread / warp index among the compute warps
+  float* red;            // [2][8] reduction scratch
+  int red_it;
+  const uint32_t* tbl;   // tile table in shared memory
+  const KindSched* sched;
+  unsigned* ctr;
+  unsigned ncta;
+  uint8_t* vs;           // vector-phase scratch (generic pointer) and its shared-window address
+  uint32_t vs_u32;
+  float* strips;         // [8 warps][192] floats: q (scaled), k_new, v_new of the unit a warp works on
+  bool attn_prefetched;  // the K/V copies of this warp's first attention unit are already in flight
+  unsigned long long* trace;
+  int trace_it;
+};
+
+__device__ __forceinline__ float compute_sum(ComputeCtx& cc, float v) {
+  v = warp_sum(v);
+  float* buf = cc.red + (cc.red_it & 1) * 8;
+  cc.red_it++;
+  if (cc.lane == 0) buf[cc.cw] = v;
+  ptx::named_bar_sync(2, kComputeThreads);
+  float r = (cc.lane < 8) ? buf[cc.lane] : 0.f;
+  return warp_sum(r);
+}
+
+__device__ __forceinline__ void stamp(ComputeCtx& cc) {
+  if (cc.trace != nullptr && cc.ct == 0) cc.trace[cc.trace_it] = ptx::globaltimer_ns();
+  cc.trace_it++;
+}
+
+// all compute threads: publish this CTA's global writes of the phase and count the CTA in.  The CTA barrier orders
+// every compute thread's stores before thread 0's gpu-scope release (the pattern of a cooperative-groups grid sync).
+// The counter is shared by all barriers (barrier #k is complete at (k + 1) * ncta arrivals), so a CTA must never arrive
+// at #k+1 before #k is complete: a CTA with GEMM work gets that from its own data dependence (epilogue <- MMA <- X
+// tiles <- poll of #k), a CTA without units of a GEMM waits explicitly.
+__device__ __forceinline__ void grid_arrive(ComputeCtx& cc, uint32_t xgo_bar) {
+  ptx::fence_proxy_async();  // this thread's generic accesses to the X ring (vector scratch) before TMA reuses it
+  ptx::named_bar_sync(1, kComputeThreads);
+  stamp(cc);
+  if (cc.ct == 0) {
+    fence_proxy_async_all();  // the global writes are read through TMA (async proxy) by other CTAs
+    red_release_add(cc.ctr, 1u);
+    if (xgo_bar != 0) ptx::mbar_arrive(xgo_bar);  // the X producer may start polling for this barrier
+  }
+}
+// all compute threads: wait until every CTA has arrived at the first `n` barriers
+__device__ __forceinline__ void grid_wait(ComputeCtx& cc, unsigned n) {
+  if (cc.ct == 0) poll_counter(cc.ctr, n * cc.ncta);
+  ptx::named_bar_sync(1, kComputeThreads);
+  stamp(cc);
+}
+
+// sum of the split-K partial slots of 4 consecutive outputs, slots added in slot order; loads issued 8 at a time
+__device__ __forceinline__ float4 sum_slots4(const float* src, uint32_t slot_stride, int nsl) {
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+  for (int s0 = 0; s0 < nsl; s0 += 8) {
+    float4 w[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) w[j] = (s0 + j < nsl) ? ldcg_f4(src + (s0 + j) * slot_stride) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      acc.x += w[j].x; acc.y += w[j].y; acc.z += w[j].z; acc.w += w[j].w;
+    }
+  }
+  return acc;
+}
+
+// h[t] = (embed | h[t] + bias + sum of split-K partials); x[t] = LayerNorm(h[t]) for the rows t = cta, cta + ncta, ...
+// The row is staged in shared memory (each thread re-reads only what it wrote).
+__device__ __noinline__ void ln_phase(const MegaParams& p, ComputeCtx& cc, int cta, bool embed, int prev_kind, const float* prev_bias,
+                                      const float* gamma, const float* beta) {
+  const int d = p.d, nq = d >> 2, R = p.R, ncta = p.ncta;
+  float4* rowbuf = reinterpret_cast<float4*>(cc.vs);
+  const uint32_t* const tbl = cc.tbl;
+  const float* const ws = p.ws;
+  float* const hbase = p.h;
+  bf16* const xbase = p.x;
+  const float eps = p.eps;
+  const int ct = cc.ct;
+  const int p_tbl_off = p.g[prev_kind].tbl_off, p_rows_out = p.g[prev_kind].rows_out;
+  for (int t = cta; t < R; t += ncta) {
+    float s = 0.f;
+    float4* hrow = reinterpret_cast<float4*>(hbase + static_cast<size_t>(t) * d);
+    if (embed) {
+      const int tok = p.debug ? 0 : p.tokens[t];  // (debug modes compute garbage: keep the gather in range)
+      const uint2* te = reinterpret_cast<const uint2*>(p.wte + static_cast<size_t>(tok) * d);
+      const uint2* pe = p.wpe ? reinterpret_cast<const uint2*>(p.wpe + static_cast<size_t>(p.ctx_len[t]) * d) : nullptr;
+#pragma unroll 1
+      for (int q = ct; q < nq; q += kComputeThreads) {
+        const uint2 e = __ldg(te + q);
+        const float2 e0 = unpack_bf16x2(e.x), e1 = unpack_bf16x2(e.y);
+        float4 a = make_float4(e0.x, e0.y, e1.x, e1.y);
+        if (pe != nullptr) {
+          const uint2 w = __ldg(pe + q);
+          const float2 w0 = unpack_bf16x2(w.x), w1 = unpack_bf16x2(w.y);
+          a.x += w0.x; a.y += w0.y; a.z += w1.x; a.w += w1.y;
+        }
+        hrow[q] = a;
+        rowbuf[q] = a;
+        s += (a.x + a.y) + (a.z + a.w);
+      }
+    } else {
+      // two columns (float4) per thread per pass, their slot loads issued together: the phase is a chain of L2
+      // round trips, so the fewer dependent ones the better
+      const uint32_t slot_stride = static_cast<uint32_t>(R) * p_rows_out;
+      const float* src = ws + static_cast<uint32_t>(t) * p_rows_out;
+#pragma unroll 1
+      for (int q0 = ct; q0 < nq; q0 += 2 * kComputeThreads) {
+        const int q1 = q0 + kComputeThreads;
+        const bool has1 = q1 < nq;
+        const int nsl0 = static_cast<int>(tbl[p_tbl_off + (q0 >> 5)] >> 16);
+        const int nsl1 = has1 ? static_cast<int>(tbl[p_tbl_off + (q1 >> 5)] >> 16) : 0;
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(prev_bias) + q0);
+        const float4 b1 = has1 ? __ldg(reinterpret_cast<const float4*>(prev_bias) + q1) : z4;
+        const float4 r0 = hrow[q0];
+        const float4 r1 = has1 ? hrow[q1] : z4;
+        float4 a0 = z4, a1 = z4;
+        const int nmax = nsl0 > nsl1 ? nsl0 : nsl1;
+#pragma unroll 1
+        for (int s0 = 0; s0 < nmax; s0 += 8) {
+          float4 w0[8], w1[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            w0[j] = (s0 + j < nsl0) ? ldcg_f4(src + (q0 << 2) + (s0 + j) * slot_stride) : z4;
+            w1[j] = (s0 + j < nsl1) ? ldcg_f4(src + (q1 << 2) + (s0 + j) * slot_stride) : z4;
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            a0.x += w0[j].x; a0.y += w0[j].y; a0.z += w0[j].z; a0.w += w0[j].w;
+            a1.x += w1[j].x; a1.y += w1[j].y; a1.z += w1[j].z; a1.w += w1[j].w;
+          }
+        }
+        const float4 o0 = make_float4(r0.x + (a0.x + b0.x), r0.y + (a0.y + b0.y), r0.z + (a0.z + b0.z), r0.w + (a0.w + b0.w));
+        hrow[q0] = o0;
+        rowbuf[q0] = o0;
+        s += (o0.x + o0.y) + (o0.z + o0.w);
+        if (has1) {
+          const float4 o1 = make_float4(r1.x + (a1.x + b1.x), r1.y + (a1.y + b1.y), r1.z + (a1.z + b1.z), r1.w + (a1.w + b1.w));
+          hrow[q1] = o1;
+          rowbuf[q1] = o1;
+          s += (o1.x + o1.y) + (o1.z + o1.w);
+        }
+      }
+    }
+    const float mean = compute_sum(cc, s) / d;
+    float qv = 0.f;
+#pragma unroll 1
+    for (int q = ct; q < nq; q += kComputeThreads) {
+      const float4 v = rowbuf[q];
+      const float a = v.x - mean, b = v.y - mean, c2 = v.z - mean, d2 = v.w - mean;
+      qv += (a * a + b * b) + (c2 * c2 + d2 * d2);
+    }
+    // gamma / beta of (up to) two columns are requested before the second reduction
+    const int qa = ct, qb = ct + kComputeThreads;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 ga = qa < nq ? __ldg(reinterpret_cast<const float4*>(gamma) + qa) : z4;
+    const float4 ba = qa < nq ? __ldg(reinterpret_cast<const float4*>(beta) + qa) : z4;
+    const float4 gb = qb < nq ? __ldg(reinterpret_cast<const float4*>(gamma) + qb) : z4;
+    const float4 bb = qb < nq ? __ldg(reinterpret_cast<const float4*>(beta) + qb) : z4;
+    const float var = compute_sum(cc, qv) / d;
+    const float rstd = rsqrtf(var + eps);
+    uint2* xr = reinterpret_cast<uint2*>(xbase + static_cast<size_t>(t) * d);
+#pragma unroll 1
+    for (int q = ct; q < nq; q += kComputeThreads) {
+      const float4 v = rowbuf[q];
+      const float4 g4 = q == qa ? ga : q == qb ? gb : __ldg(reinterpret_cast<const float4*>(gamma) + q);
+      const float4 b4 = q == qa ? ba : q == qb ? bb : __ldg(reinterpret_cast<const float4*>(beta) + q);
+      uint2 pk;
+      pk.x = pack_bf16x2((v.x - mean) * rstd * g4.x + b4.x, (v.y - mean) * rstd * g4.y + b4.y);
+      pk.y = pack_bf16x2((v.z - mean) * rstd * g4.z + b4.z, (v.w - mean) * rstd * g4.w + b4.w);
+      xr[q] = pk;
+    }
+  }
+}
+
+// mlp[t, f] = gelu_new(sum of c_fc partials + bias)
+__device__ __noinline__ void gelu_phase(const MegaParams& p, ComputeCtx& cc, int cta, const float* bias) {
+  const uint32_t rows_out = p.g[2].rows_out, tbl_off = p.g[2].tbl_off;
+  const uint32_t nq = rows_out >> 2;
+  const uint32_t total = static_cast<uint32_t>(p.R) * nq;
+  const uint32_t slot_stride = static_cast<uint32_t>(p.R) * rows_out;
+  const uint32_t step = static_cast<uint32_t>(p.ncta) * kComputeThreads;
+  const uint32_t* const tbl = cc.tbl;
+  const float* const ws = p.ws;
+  bf16* const mlp = p.mlp;
+#pragma unroll 1
+  for (uint32_t idx = static_cast<uint32_t>(cta) * kComputeThreads + cc.ct; idx < total; idx += step) {
+    const uint32_t t = idx / nq, q = idx - t * nq;
+    const int nsl = static_cast<int>(tbl[tbl_off + (q >> 5)] >> 16);
+    const float4 acc = sum_slots4(ws + (t * rows_out + (q << 2)), slot_stride, nsl);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + q);
+    float o[4] = {acc.x + b.x, acc.y + b.y, acc.z + b.z, acc.w + b.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      // same form as the GEMM epilogue's gelu_new: 0.5 x (1 + tanh(u)) == x - x / (1 + exp(2u))
+      const float xx = o[k];
+      const float u = 0.7978845608028654f * (xx + 0.044715f * xx * xx * xx);
+      o[k] = xx - __fdividef(xx, 1.f + __expf(2.f * u));
+    }
+    uint2 pk;
+    pk.x = pack_bf16x2(o[0], o[1]);
+    pk.y = pack_bf16x2(o[2], o[3]);
+    *(reinterpret_cast<uint2*>(mlp + t * rows_out) + q) = pk;
+  }
+}
+
+// One warp per (row, head), head_dim 64.  q/k/v = bf16(sum of c_attn partials + bias); the new k/v are appended to
+// the cache; softmax(q K^T) V over the cached tokens and the new one.
+// The phase is latency bound (8 warps per SM, a few dependent memory round trips each), so the K/V rows travel by
+// cp.async into the warp's 8 KB slice of the idle X ring -- no registers are held while they are in flight, which
+// keeps ptxas from serialising the loads -- in batches of 16 tokens, two batches in flight; the sum of the c_attn
+// partials is computed underneath.  lane = (token group g = lane / 8, 16-byte chunk c = lane % 8); the batches are
+// folded with an online softmax.  page_tokens is a power of two (host-checked); offsets are 32-bit element offsets.
+// prefetch_only: issue the K/V copies of this warp's first unit and return (called between the arrival at the c_attn
+// barrier and the wait for it: cached K/V do not depend on the current step, so their latency hides behind the
+// barrier); the phase proper then skips that issue (cc.attn_prefetched).
+__device__ __noinline__ void attention_phase(const MegaParams& p, ComputeCtx& cc, int cta, int layer, const float* bias, bool prefetch_only) {
+  constexpr int HD = 64;
+  const int rows_out = p.g[0].rows_out, tbl_off = p.g[0].tbl_off;
+  const int d = p.d, H = p.H, lane = cc.lane, ncta = p.ncta, cw = cc.cw;
+  const int grp = lane >> 3, ch = lane & 7;
+  const KvCache cache = p.kv;
+  const uint32_t* const tbl = cc.tbl;
+  const float* const ws = p.ws;
+  bf16* const att = p.att;
+  const int* const ctx_len = p.ctx_len;
+  const int* const block_table = p.block_table;
+  const float scale = p.scale;
+  const uint32_t stage_u32 = cc.vs_u32 + cw * 8192;   // [2 halves][K 16 x 128 B | V 16 x 128 B]
+  float* qkvs = cc.strips + cw * 192;
+  const int total = p.R * H;
+  const uint32_t slot_stride = static_cast<uint32_t>(p.R) * rows_out;
+  const int lpt = p.log2_page_tokens, ptm = (1 << lpt) - 1;
+  const uint32_t page_stride = static_cast<uint32_t>(H) << (lpt + 6);   // elements per page (all heads)
+  const size_t kv_stride = static_cast<size_t>(cache.num_pages) * page_stride;
+  const bf16* layer_k = cache.base + static_cast<size_t>(layer) * 2 * kv_stride;
+  const uint32_t lane_dst = static_cast<uint32_t>(grp) * 128u + static_cast<uint32_t>(ch) * 16u;
+#pragma unroll 1
+  for (int unit = cw * ncta + cta; unit < total; unit += 8 * ncta) {
+    const int b = unit / H, h = unit - b * H;
+    const int ctx = ctx_len[b];
+    const int* bt = block_table + static_cast<uint32_t>(b) * cache.max_pages_per_row;
+    const int npages = (ctx >> lpt) + 1;  // pages holding positions [0, ctx]
+    // page ids: one coalesced load when they fit a warp (always for 16-token pages), else per-token lookups
+    const bool pages_in_warp = npages <= 32;
+    const int my_page = (pages_in_warp && lane < npages) ? bt[lane] : 0;
+    const bf16* kbase = layer_k + (static_cast<uint32_t>(h) << (lpt + 6)) + ch * 8;  // + page * page_stride + (t & ptm) * 64
+    const int nb = (ctx + 15) >> 4;
+
+    auto issue = [&](int bi) {
+      const uint32_t dst = stage_u32 + static_cast<uint32_t>(bi & 1) * 4096u + lane_dst;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int t = bi * 16 + i * 4 + grp;
+        const bool ok = t < ctx;
+        const int tt = ok ? t : 0;
+        const int page = pages_in_warp ? __shfl_sync(0xffffffffu, my_page, tt >> lpt) : bt[tt >> lpt];
+        const bf16* kp = kbase + (static_cast<uint32_t>(page) * page_stride + (static_cast<uint32_t>(tt & ptm) << 6));
+        cp_async16(dst + i * 512u, kp, ok ? 16u : 0u);
+        cp_async16(dst + i * 512u + 2048u, kp + kv_stride, ok ? 16u : 0u);
+      }
+      cp_async_commit();
+    };
+    if (!cc.attn_prefetched) {
+      if (nb > 0) issue(0);
+      if (nb > 1) issue(1);
+    }
+    cc.attn_prefetched = false;
+    if (prefetch_only) {
+      cc.attn_prefetched = true;
+      return;
+    }
+
+    // ---- q / k_new / v_new while the first batches are in flight: lane owns dims (2 lane, 2 lane + 1) of each
+    {
+      const int dim = lane * 2;
+      const float* src0 = ws + static_cast<uint32_t>(b) * rows_out + h * HD + dim;
+      float2 w[3][8];
+      int nsl[3];
+#pragma unroll
+      for (int pz = 0; pz < 3; ++pz) {
+        nsl[pz] = static_cast<int>(tbl[tbl_off + ((pz * d + h * HD) >> 7)] >> 16);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          w[pz][j] = (j < nsl[pz]) ? ldcg_f2(src0 + pz * d + j * slot_stride) : make_float2(0.f, 0.f);
+      }
+      float2 part[3];
+#pragma unroll
+      for (int pz = 0; pz < 3; ++pz) {
+        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc.x += w[pz][j].x; acc.y += w[pz][j].y;
+        }
+        for (int sl = 8; sl < nsl[pz]; ++sl) {  // (more than 8 contributors per tile: tiny K only)
+          const float2 e = ldcg_f2(src0 + pz * d + sl * slot_stride);
+          acc.x += e.x; acc.y += e.y;
+        }
+        const float2 bb = __ldg(reinterpret_cast<const float2*>(bias + pz * d + h * HD + dim));
+        // the operator-per-kernel path stores c_attn's output as bf16: keep the same rounding
+        part[pz] = unpack_bf16x2(pack_bf16x2(acc.x + bb.x, acc.y + bb.y));
+      }
+      __syncwarp();  // the previous unit's reads of qkvs are complete
+      *reinterpret_cast<float2*>(qkvs + dim) = make_float2(part[0].x * scale, part[0].y * scale);
+      *reinterpret_cast<float2*>(qkvs + HD + dim) = part[1];
+      *reinterpret_cast<float2*>(qkvs + 2 * HD + dim) = part[2];
+      __syncwarp();
+    }
+    float q8[8], acc[8];
+    {
+      const float4 a0 = *reinterpret_cast<const float4*>(qkvs + ch * 8), a1 = *reinterpret_cast<const float4*>(qkvs + ch * 8 + 4);
+      q8[0] = a0.x; q8[1] = a0.y; q8[2] = a0.z; q8[3] = a0.w; q8[4] = a1.x; q8[5] = a1.y; q8[6] = a1.z; q8[7] = a1.w;
+    }
+    // the new token: score, and its k / v chunks go to the cache (group 0 writes k, group 1 writes v)
+    float m_run, l_run;
+    {
+      const float4 k0 = *reinterpret_cast<const float4*>(qkvs + HD + ch * 8), k1 = *reinterpret_cast<const float4*>(qkvs + HD + ch * 8 + 4);
+      const float4 v0 = *reinterpret_cast<const float4*>(qkvs + 2 * HD + ch * 8), v1 = *reinterpret_cast<const float4*>(qkvs + 2 * HD + ch * 8 + 4);
+      float sn = q8[0] * k0.x;
+      sn = fmaf(q8[1], k0.y, sn); sn = fmaf(q8[2], k0.z, sn); sn = fmaf(q8[3], k0.w, sn);
+      sn = fmaf(q8[4], k1.x, sn); sn = fmaf(q8[5], k1.y, sn); sn = fmaf(q8[6], k1.z, sn); sn = fmaf(q8[7], k1.w, sn);
+      sn += __shfl_xor_sync(0xffffffffu, sn, 1);
+      sn += __shfl_xor_sync(0xffffffffu, sn, 2);
+      sn += __shfl_xor_sync(0xffffffffu, sn, 4);
+      m_run = sn;
+      const bool g0 = grp == 0;
+      l_run = g0 ? 1.f : 0.f;
+      acc[0] = g0 ? v0.x : 0.f; acc[1] = g0 ? v0.y : 0.f; acc[2] = g0 ? v0.z : 0.f; acc[3] = g0 ? v0.w : 0.f;
+      acc[4] = g0 ? v1.x : 0.f; acc[5] = g0 ? v1.y : 0.f; acc[6] = g0 ? v1.z : 0.f; acc[7] = g0 ? v1.w : 0.f;
+      const int page_new = pages_in_warp ? __shfl_sync(0xffffffffu, my_page, ctx >> lpt) : bt[ctx >> lpt];
+      if (grp < 2) {
+        const float4 s0 = g0 ? k0 : v0, s1 = g0 ? k1 : v1;
+        uint4 pk;
+        pk.x = pack_bf16x2(s0.x, s0.y); pk.y = pack_bf16x2(s0.z, s0.w); pk.z = pack_bf16x2(s1.x, s1.y); pk.w = pack_bf16x2(s1.z, s1.w);
+        const uint32_t off = static_cast<uint32_t>(page_new) * page_stride + (static_cast<uint32_t>(ctx & ptm) << 6);
+        *reinterpret_cast<uint4*>(const_cast<bf16*>(kbase) + off + (g0 ? 0 : kv_stride)) = pk;
+      }
+    }
+    // ---- cached tokens, 16 per batch
+#pragma unroll 1
+    for (int bi = 0; bi < nb; ++bi) {
+      if (bi + 1 < nb) cp_async_wait<1>(); else cp_async_wait<0>();
+      __syncwarp();
+      const uint32_t src = stage_u32 + static_cast<uint32_t>(bi & 1) * 4096u + lane_dst;
+      uint4 kk[4], vv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        kk[i] = lds_u4(src + i * 512u);
+        vv[i] = lds_u4(src + i * 512u + 2048u);
+      }
+      __syncwarp();                      // every lane has read the half: it may be refilled
+      if (bi + 2 < nb) issue(bi + 2);
+      float sc[4];
+      float m_b = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 k0 = unpack_bf16x2(kk[i].x), k1 = unpack_bf16x2(kk[i].y), k2 = unpack_bf16x2(kk[i].z), k3 = unpack_bf16x2(kk[i].w);
+        float s = q8[0] * k0.x;
+        s = fmaf(q8[1], k0.y, s); s = fmaf(q8[2], k1.x, s); s = fmaf(q8[3], k1.y, s);
+        s = fmaf(q8[4], k2.x, s); s = fmaf(q8[5], k2.y, s); s = fmaf(q8[6], k3.x, s); s = fmaf(q8[7], k3.y, s);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        sc[i] = (bi * 16 + i * 4 + grp < ctx) ? s : -INFINITY;
+        m_b = fmaxf(m_b, sc[i]);
+      }
+      m_b = fmaxf(m_b, __shfl_xor_sync(0xffffffffu, m_b, 8));
+      m_b = fmaxf(m_b, __shfl_xor_sync(0xffffffffu, m_b, 16));
+      const float m_new = fmaxf(m_run, m_b);
+      const float resc = __expf(m_run - m_new);
+      m_run = m_new;
+      l_run *= resc;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] *= resc;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float pr = __expf(sc[i] - m_new);  // exp(-inf) = 0 for masked tokens (their V rows were zero-filled)
+        l_run += pr;
+        const float2 v0 = unpack_bf16x2(vv[i].x), v1 = unpack_bf16x2(vv[i].y), v2 = unpack_bf16x2(vv[i].z), v3 = unpack_bf16x2(vv[i].w);
+        acc[0] = fmaf(pr, v0.x, acc[0]); acc[1] = fmaf(pr, v0.y, acc[1]); acc[2] = fmaf(pr, v1.x, acc[2]); acc[3] = fmaf(pr, v1.y, acc[3]);
+        acc[4] = fmaf(pr, v2.x, acc[4]); acc[5] = fmaf(pr, v2.y, acc[5]); acc[6] = fmaf(pr, v3.x, acc[6]); acc[7] = fmaf(pr, v3.y, acc[7]);
+      }
+    }
+    // fold the 4 token groups
+    l_run += __shfl_xor_sync(0xffffffffu, l_run, 8);
+    l_run += __shfl_xor_sync(0xffffffffu, l_run, 16);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 8);
+      acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 16);
+    }
+    if (grp == 0) {
+      const float inv = 1.f / l_run;
+      uint4 pk;
+      pk.x = pack_bf16x2(acc[0] * inv, acc[1] * inv); pk.y = pack_bf16x2(acc[2] * inv, acc[3] * inv);
+      pk.z = pack_bf16x2(acc[4] * inv, acc[5] * inv); pk.w = pack_bf16x2(acc[6] * inv, acc[7] * inv);
+      *reinterpret_cast<uint4*>(att + static_cast<uint32_t>(b) * d + h * HD + ch * 8) = pk;
+    }
+  }
+}
+
+struct EpiCtx {
+  uint32_t tmem_base, t_full0, t_empty0;  // barrier b at +8 b
+  uint32_t ait;                           // accumulator buffers consumed so far
+};
+
+// TMEM accumulator -> fp32 split-K partial in the workspace, for every segment of this CTA in GEMM `kind`.
+// Compute warp w reads TMEM lane quadrant w % 4 (its hardware-accessible quarter) and column half w / 4.
+__device__ __noinline__ void epilogue_phase(const MegaParams& p, ComputeCtx& cc, EpiCtx& ec, int cta, int kind, int layer) {
+  if ((p.debug & 1) != 0) return;
+  // every field used below is copied to a register first: the partial stores could alias anything reached through
+  // the references, and a reload per store costs more than the store
+  const int rows_out = p.g[kind].rows_out, tbl_off = p.g[kind].tbl_off;
+  const int R = p.R, N = p.N;
+  float* const ws = p.ws;
+  const uint32_t* const tbl = cc.tbl;
+  const KindSched sc = cc.sched[kind];
+  const uint32_t tmem_base = ec.tmem_base, t_full0 = ec.t_full0, t_empty0 = ec.t_empty0;
+  uint32_t ait = ec.ait;
+  const int lane = cc.lane, quad = cc.cw & 3, half = cc.cw >> 2;
+  const bool stamp0 = cc.ct == 0;
+  const int c_beg = half * (N >> 1);
+  int c_end = (half + 1) * (N >> 1);
+  if (c_end > R) c_end = R;
+  const bool wide = ((N >> 1) & 31) == 0;
+  int n = sc.n, tile = sc.tile0, kb = sc.kb0;
+#pragma unroll 1
+  while (n > 0) {
+    int len = sc.kb - kb;
+    if (len > n) len = n;
+    const uint32_t buf = ait & 1, aph = (ait >> 1) & 1;
+    ++ait;
+    ptx::mbar_wait(t_full0 + 8u * buf, aph);
+    ptx::tc_fence_after();
+    if (stamp0) MEGA_RSTAMP(layer, kind * 8 + 4);
+    const int slot = cta - static_cast<int>(tbl[tbl_off + tile] & 0xffffu);
+    const int i = tile * 128 + quad * 32 + lane;
+    const bool i_ok = i < rows_out;
+    float* dst = ws + (static_cast<size_t>(slot) * R + c_beg) * rows_out + i;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + buf * static_cast<uint32_t>(N);
+    if (wide) {
+#pragma unroll 1
+      for (int c0 = c_beg; c0 < c_end; c0 += 32) {
+        uint32_t r[32];
+        ptx::tmem_ld32(taddr + c0, r);
+        ptx::tmem_ld_wait();
+        if (i_ok) {
+          if (c0 + 32 <= c_end) {
+#pragma unroll
+            for (int v = 0; v < 32; ++v) dst[static_cast<size_t>(v) * rows_out] = __uint_as_float(r[v]);
+          } else {
+#pragma unroll
+            for (int v = 0; v < 32; ++v)
+              if (c0 + v < c_end) dst[static_cast<size_t>(v) * rows_out] = __uint_as_float(r[v]);
+          }
+        }
+        dst += static_cast<size_t>(32) * rows_out;
+      }
+    } else {
+#pragma unroll 1
+      for (int c0 = c_beg; c0 < c_end; c0 += 8) {
+        uint32_t r[8];
+        ptx::tmem_ld8(taddr + c0, r);
+        ptx::tmem_ld_wait();
+        if (i_ok) {
+#pragma unroll
+          for (int v = 0; v < 8; ++v)
+            if (c0 + v < c_end) dst[static_cast<size_t>(v) * rows_out] = __uint_as_float(r[v]);
+        }
+        dst += static_cast<size_t>(8) * rows_out;
+      }
+    }
+    ptx::tc_fence_before();
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(t_empty0 + 8u * buf);
+    if (stamp0) MEGA_RSTAMP(layer, kind * 8 + 5);
+    n -= len;
+    kb = 0;
+    ++tile;
+  }
+  ec.ait = ait;
+}
+
+__global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const __grid_constant__ CUtensorMap xmap_x,
+                                                                  const __grid_constant__ CUtensorMap xmap_att,
+                                                                  const __grid_constant__ CUtensorMap xmap_mlp,
+                                                                  const __grid_constant__ MegaParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_u32 = ptx::smem_u32(smem_raw);
+  const uint32_t base = (raw_u32 + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - raw_u32);
+  const int nW = p.nW, nX = p.nX;
+  const uint32_t xstage = static_cast<uint32_t>(p.N) * 128u;
+  const uint32_t w_ring = base;
+  const uint32_t x_ring = w_ring + nW * kWStage;
+  // after the X ring (>= kVecScratch bytes): q/k/v strips (8 x 192 floats), reduction scratch, schedule, tile table, barriers
+  const uint32_t misc_off = nW * kWStage + p.xring_bytes;
+  float* strips = reinterpret_cast<float*>(gen + misc_off);
+  float* red = reinterpret_cast<float*>(gen + misc_off + 8 * 192 * 4);
+  KindSched* sched = reinterpret_cast<KindSched*>(gen + misc_off + 8 * 192 * 4 + 64);
+  uint32_t* tbl = reinterpret_cast<uint32_t*>(gen + misc_off + 8 * 192 * 4 + 64 + 64);
+  const uint32_t bar_off = misc_off + 8 * 192 * 4 + 64 + 64 + kTblMax * 4;
+  const uint32_t bars = base + bar_off;
+  // barrier layout: w_full[nW], w_empty[nW], x_full[nX], x_empty[nX], t_full[2], t_empty[2], xgo, tmem slot
+  const uint32_t w_full0 = bars, w_empty0 = bars + 8u * nW;
+  const uint32_t x_full0 = bars + 16u * nW, x_empty0 = x_full0 + 8u * nX;
+  const uint32_t t_full0 = x_empty0 + 8u * nX, t_empty0 = t_full0 + 16u;
+  const uint32_t xgo = t_empty0 + 16u;  // compute -> X producer: "this CTA arrived at the barrier you need"
+  const uint32_t tmem_slot = xgo + 8u;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cta = blockIdx.x, ncta = p.ncta;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < nW; ++s) {
+      ptx::mbar_init(w_full0 + 8u * s, 1);
+      ptx::mbar_init(w_empty0 + 8u * s, 1);
+    }
+    for (int s = 0; s < nX; ++s) {
+      ptx::mbar_init(x_full0 + 8u * s, 1);
+      ptx::mbar_init(x_empty0 + 8u * s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(t_full0 + 8u * b, 1);
+      ptx::mbar_init(t_empty0 + 8u * b, 8);
+    }
+    ptx::mbar_init(xgo, 1);
+    ptx::fence_mbar_init();
+  }
+  if (threadIdx.x >= 32 && threadIdx.x < 36) {
+    const int kind = threadIdx.x - 32;
+    const MegaGemmShape& g = p.g[kind];
+    // few units (small models): only the first `units` CTAs take part, so that the contributors of a row tile
+    // are consecutive CTAs (slot = cta - first contributor)
+    const int nc = g.units < ncta ? g.units : ncta;
+    const int u0 = cta < nc ? static_cast<int>(static_cast<long long>(cta) * g.units / nc) : 0;
+    const int u1 = cta < nc ? static_cast<int>(static_cast<long long>(cta + 1) * g.units / nc) : 0;
+    KindSched k;
+    k.n = u1 - u0;
+    k.tile0 = u0 / g.kb;
+    k.kb0 = u0 - k.tile0 * g.kb;
+    k.kb = g.kb;
+    sched[kind] = k;
+  }
+  if (warp == 3) ptx::tmem_alloc<512>(tmem_slot);
+  for (int i = threadIdx.x; i < p.tbl_entries; i += kThreads) tbl[i] = p.tile_tbl[i];
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const bool skip_gemm = (p.debug & 1) != 0;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ W producer
+    // (the whole warp walks the schedule and waits; one elected lane issues: converged code lets the compiler emit
+    //  the single-thread instructions without a per-instruction election loop)
+    if (!skip_gemm) {
+      uint32_t s = 0, ph = 0;
+#pragma unroll 1
+      for (int l = 0; l < p.L; ++l) {
+#pragma unroll 1
+        for (int kind = 0; kind < 4; ++kind) {
+          const CUtensorMap* wm = p.wmaps + (l * 4 + kind);
+          const KindSched sc = sched[kind];
+          int tile = sc.tile0, kb = sc.kb0;
+#pragma unroll 1
+          for (int n = sc.n; n > 0; --n) {
+            ptx::mbar_wait(w_empty0 + 8u * s, ph ^ 1);
+            if (ptx::elect_one()) {
+              ptx::mbar_arrive_expect_tx(w_full0 + 8u * s, kWStage);
+              ptx::tma_load_2d(w_ring + s * kWStage, wm, w_full0 + 8u * s, kb * 64, tile * 128, ptx::kEvictFirst);
+            }
+            __syncwarp();
+            if (++s == static_cast<uint32_t>(nW)) { s = 0; ph ^= 1; }
+            if (++kb == sc.kb) { kb = 0; ++tile; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ X producer
+    if (!skip_gemm) {
+      uint32_t s = 0, ph = 0;
+#pragma unroll 1
+      for (int l = 0; l < p.L; ++l) {
+#pragma unroll 1
+        for (int kind = 0; kind < 4; ++kind) {
+          const CUtensorMap* xm = (kind == 1) ? &xmap_att : (kind == 3) ? &xmap_mlp : &xmap_x;
+          const KindSched sc = sched[kind];
+          if (sc.n == 0) continue;
+          // the activation is complete once every CTA passed barrier #(8l + 2 kind) (the vector phase before it);
+          // no point in polling before this CTA's own compute warps arrived there (their (4l + kind)-th signal)
+          ptx::mbar_wait(xgo, static_cast<uint32_t>(4 * l + kind) & 1u);
+          if (lane == 0) {
+            poll_counter(p.sync, static_cast<unsigned>(8 * l + 2 * kind + 1) * ncta);
+            fence_proxy_async_all();
+            MEGA_RSTAMP(l, kind * 8 + 0);
+          }
+          __syncwarp();
+          int kb = sc.kb0;
+#pragma unroll 1
+          for (int n = sc.n; n > 0; --n) {
+            ptx::mbar_wait(x_empty0 + 8u * s, ph ^ 1);
+            if (lane == 0) {
+              ptx::mbar_arrive_expect_tx(x_full0 + 8u * s, xstage);
+              ptx::tma_load_2d(x_ring + s * xstage, xm, x_full0 + 8u * s, kb * 64, 0, ptx::kEvictLast);
+            }
+            __syncwarp();
+            if (++s == static_cast<uint32_t>(nX)) { s = 0; ph ^= 1; }
+            if (++kb == sc.kb) kb = 0;
+          }
+          if (lane == 0) MEGA_RSTAMP(l, kind * 8 + 1);
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (!skip_gemm) {
+      const uint32_t idesc = ptx::umma_idesc_bf16(128, p.N);
+      const uint64_t wdesc0 = ptx::umma_desc_k_sw128(w_ring), xdesc0 = ptx::umma_desc_k_sw128(x_ring);
+      uint32_t ws = 0, wph = 0, xs = 0, xph = 0, ait = 0;
+#pragma unroll 1
+      for (int l = 0; l < p.L; ++l) {
+#pragma unroll 1
+        for (int kind = 0; kind < 4; ++kind) {
+          const KindSched sc = sched[kind];
+          int n = sc.n, kb = sc.kb0;
+#pragma unroll 1
+          while (n > 0) {
+            int len = sc.kb - kb;
+            if (len > n) len = n;
+            const uint32_t buf = ait & 1, aph = (ait >> 1) & 1;
+            ++ait;
+            ptx::mbar_wait(t_empty0 + 8u * buf, aph ^ 1);
+            ptx::tc_fence_after();
+            const uint32_t tacc = tmem_base + buf * static_cast<uint32_t>(p.N);
+#pragma unroll 1
+            for (int j = 0; j < len; ++j) {
+              ptx::mbar_wait(w_full0 + 8u * ws, wph);
+              ptx::mbar_wait(x_full0 + 8u * xs, xph);
+              ptx::tc_fence_after();
+              if (ptx::elect_one()) {
+                if (j == 0) MEGA_RSTAMP(l, kind * 8 + 2);
+                const uint64_t adesc = wdesc0 + static_cast<uint64_t>((ws * kWStage) >> 4);
+                const uint64_t bdesc = xdesc0 + static_cast<uint64_t>((xs * xstage) >> 4);
+                ptx::umma_bf16(tacc, adesc, bdesc, idesc, j > 0 ? 1u : 0u);
+                ptx::umma_bf16(tacc, adesc + 2u, bdesc + 2u, idesc, 1u);
+                ptx::umma_bf16(tacc, adesc + 4u, bdesc + 4u, idesc, 1u);
+                ptx::umma_bf16(tacc, adesc + 6u, bdesc + 6u, idesc, 1u);
+                ptx::umma_commit(w_empty0 + 8u * ws);
+                ptx::umma_commit(x_empty0 + 8u * xs);
+                if (j == len - 1) {
+                  ptx::umma_commit(t_full0 + 8u * buf);
+                  MEGA_RSTAMP(l, kind * 8 + 3);
+                }
+              }
+              __syncwarp();
+              if (++ws == static_cast<uint32_t>(nW)) { ws = 0; wph ^= 1; }
+              if (++xs == static_cast<uint32_t>(nX)) { xs = 0; xph ^= 1; }
+            }
+            n -= len;
+            kb = 0;
+          }
+        }
+      }
+    }
+  } else if (warp >= kComputeWarp0) {
+    // ------------------------------------------------------------------ compute warps
+    ComputeCtx cc;
+    cc.ct = threadIdx.x - kComputeWarp0 * 32;
+    cc.cw = warp - kComputeWarp0;
+    cc.lane = lane;
+    cc.red = red;
+    cc.red_it = 0;
+    cc.tbl = tbl;
+    cc.sched = sched;
+    cc.ctr = p.sync;
+    cc.ncta = ncta;
+    cc.vs = gen + nW * kWStage;
+    cc.vs_u32 = x_ring;
+    cc.strips = strips;
+    cc.attn_prefetched = false;
+    cc.trace = p.trace ? p.trace + static_cast<size_t>(cta) * (2 * (8 * p.L + 2)) : nullptr;
+    cc.trace_it = 0;
+    EpiCtx ec;
+    ec.tmem_base = tmem_base;
+    ec.t_full0 = t_full0;
+    ec.t_empty0 = t_empty0;
+    ec.ait = 0;
+
+#pragma unroll 1
+    for (int l = 0; l < p.L; ++l) {
+      const MegaLayer ly = p.layers[l];
+      if (l > 0) grid_wait(cc, 8 * l);
+      ln_phase(p, cc, cta, l == 0, 3, l > 0 ? p.layers[l - 1].b_fc2 : nullptr, ly.ln1_g, ly.ln1_b);
+      grid_arrive(cc, xgo);     // #8l
+      epilogue_phase(p, cc, ec, cta, 0, l);
+      if (sched[0].n == 0) grid_wait(cc, 8 * l + 1);  // (see grid_arrive: no arrival at #k+1 before #k is complete)
+      grid_arrive(cc, 0);       // #8l+1
+      if ((p.debug & 4) == 0) attention_phase(p, cc, cta, l, ly.b_qkv, true);
+      grid_wait(cc, 8 * l + 2);
+      attention_phase(p, cc, cta, l, ly.b_qkv, false);
+      grid_arrive(cc, xgo);     // #8l+2
+      epilogue_phase(p, cc, ec, cta, 1, l);
+      if (sched[1].n == 0) grid_wait(cc, 8 * l + 3);  // (see grid_arrive: no arrival at #k+1 before #k is complete)
+      grid_arrive(cc, 0);       // #8l+3
+      grid_wait(cc, 8 * l + 4);
+      ln_phase(p, cc, cta, false, 1, ly.b_proj, ly.ln2_g, ly.ln2_b);
+      grid_arrive(cc, xgo);     // #8l+4
+      epilogue_phase(p, cc, ec, cta, 2, l);
+      if (sched[2].n == 0) grid_wait(cc, 8 * l + 5);  // (see grid_arrive: no arrival at #k+1 before #k is complete)
+      grid_arrive(cc, 0);       // #8l+5
+      grid_wait(cc, 8 * l + 6);
+      gelu_phase(p, cc, cta, ly.b_fc);
+      grid_arrive(cc, xgo);     // #8l+6
+      epilogue_phase(p, cc, ec, cta, 3, l);
+      if (sched[3].n == 0) grid_wait(cc, 8 * l + 7);  // (see grid_arrive: no arrival at #k+1 before #k is complete)
+      grid_arrive(cc, 0);       // #8l+7
+    }
+    grid_wait(cc, 8 * p.L);
+    ln_phase(p, cc, cta, false, 3, p.layers[p.L - 1].b_fc2, p.lnf_g, p.lnf_b);
+    grid_arrive(cc, 0);         // #8L: exit barrier; CTA 0 re-arms the counter for the next launch
+    if (cta == 0 && cc.ct == 0) {
+      poll_counter(p.sync, static_cast<unsigned>(8 * p.L + 1) * ncta);
+      *reinterpret_cast<volatile unsigned*>(p.sync) = 0u;
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 3) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace
+
+size_t mega_plan(MegaState& m, int d, int ff, int ncta) {
+  const int rows[4] = {3 * d, d, ff, d};
+  const int ks[4] = {d, d, d, ff};
+  m.ncta = ncta;
+  m.h_tbl.clear();
+  size_t ws_per_row = 0;
+  for (int k = 0; k < 4; ++k) {
+    MegaGemmShape& g = m.g[k];
+    g.rows_out = rows[k];
+    g.kb = ks[k] / 64;
+    g.tiles = (rows[k] + 127) / 128;
+    g.units = g.tiles * g.kb;
+    g.tbl_off = static_cast<int>(m.h_tbl.size());
+    int max_slots = 1;
+    for (int t = 0; t < g.tiles; ++t) {
+      // contributors of tile t: CTAs whose range [c*U/n, (c+1)*U/n) intersects [t*kb, (t+1)*kb)
+      int first = -1, last = -1;
+      const int nc = g.units < ncta ? g.units : ncta;  // CTAs taking part in this kind (see KindSched setup in the kernel)
+      for (int c = 0; c < nc; ++c) {
+        const long long u0 = static_cast<long long>(c) * g.units / nc, u1 = static_cast<long long>(c + 1) * g.units / nc;
+        if (u0 < static_cast<long long>(t + 1) * g.kb && u1 > static_cast<long long>(t) * g.kb) {
+          if (first < 0) first = c;
+          last = c;
+        }
+      }
+      const int ns = last - first + 1;
+      if (ns > max_slots) max_slots = ns;
+      m.h_tbl.push_back(static_cast<uint32_t>(first) | (static_cast<uint32_t>(ns) << 16));
+    }
+    const size_t need = static_cast<size_t>(max_slots) * g.rows_out;
+    if (need > ws_per_row) ws_per_row = need;
+  }
+  m.tbl_entries = static_cast<int>(m.h_tbl.size());
+  m.ws_floats_per_row = ws_per_row;
+  return ws_per_row;
+}
+
+int mega_init() {
+  cudaError_t e = cudaFuncSetAttribute(decode_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  return e == cudaSuccess ? 0 : static_cast<int>(e);
+}
+
+int mega_launch(const MegaParams& p_in, cudaStream_t s) {
+  MegaParams p = p_in;
+  if (p.tbl_entries > kTblMax || p.d > 4096 || p.d % 8 || p.N > 256 || p.N % 16 || p.R > p.N) return static_cast<int>(cudaErrorInvalidValue);
+  // shared memory budget: W ring + X ring (doubles as the vector phases' scratch) + strips / tables / barriers
+  const int total = 227 * 1024 - 1024 /*alignment*/;
+  const int xstage = p.N * 128;
+  const int fixed = 8 * 192 * 4 + 64 + 64 + kTblMax * 4 + 512;
+  p.nX = p.N <= 64 ? 8 : p.N <= 128 ? 4 : 3;
+  p.xring_bytes = p.nX * xstage > kVecScratch ? p.nX * xstage : kVecScratch;
+  p.nW = (total - fixed - p.xring_bytes) / kWStage;
+  if (p.nW > 12) p.nW = 12;
+  if (p.nW < 2) return static_cast<int>(cudaErrorInvalidValue);
+  {
+    const char* dbg = getenv("CCB_MEGA_DEBUG");
+    p.debug = dbg ? atoi(dbg) : 0;
+    const char* lay = getenv("CCB_MEGA_LAYERS");  // tuning / debugging only: run the first n layers
+    if (lay && atoi(lay) > 0 && atoi(lay) < p.L) p.L = atoi(lay);
+  }
+  const size_t smem = static_cast<size_t>(p.nW) * kWStage + p.xring_bytes + fixed + 1024;
+
+  CUtensorMap mx, ma, mm;
+  if (gemm_make_tmap(&mx, p.x, p.R, p.d, p.d, p.N)) return -1;
+  if (gemm_make_tmap(&ma, p.att, p.R, p.d, p.d, p.N)) return -1;
+  if (gemm_make_tmap(&mm, p.mlp, p.R, p.ff, p.ff, p.N)) return -1;
+
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(p.ncta);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;  // all CTAs co-resident: they wait on one another
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, decode_mega_kernel, mx, ma, mm, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return static_cast<int>(e);
+  }
+  return 0;
+}
+
+}  // namespace ccb

@@ -6,6 +6,7 @@
 // decode step on an internal stream that is fenced against the caller's stream with events).
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -339,9 +340,64 @@ int lm_logits(ccb_ctx* c, int B, int S, int last_only, float* logits_out, int64_
 }
 
 // one token per row: embeds next_tokens at position ctx_len, runs all layers against the paged KV cache
+bool mega_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("CCB_MEGA");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
+// the whole layer stack of one decode step as ONE persistent kernel (decode_mega.cu): leaves ln_f(h) in c->x
+int lm_decode_layers_mega(ccb_ctx* c, int rows, cudaStream_t s) {
+  const ccb_model_desc& D = c->desc;
+  const MegaState& m = c->mega;
+  MegaParams p;
+  memset(&p, 0, sizeof(p));
+  p.L = D.lm_layers;
+  p.d = D.lm_d;
+  p.H = D.lm_heads;
+  p.ff = 4 * D.lm_d;
+  p.R = rows;
+  p.N = (rows + 15) / 16 * 16;
+  p.ncta = m.ncta;
+  p.eps = D.lm_ln_eps;
+  p.scale = 1.0f / sqrtf(static_cast<float>(D.lm_d / D.lm_heads));
+  p.layers = m.d_layers;
+  p.wmaps = m.d_wmaps;
+  p.tile_tbl = m.d_tbl;
+  p.tbl_entries = m.tbl_entries;
+  for (int k = 0; k < 4; ++k) p.g[k] = m.g[k];
+  p.h = c->h;
+  p.x = c->x;
+  p.att = c->att;
+  p.mlp = c->mlp;
+  p.ws = m.d_ws;
+  p.wte = c->wte;
+  p.wpe = c->wpe;
+  p.tokens = c->next_tokens;
+  p.ctx_len = c->ctx_len;
+  p.block_table = c->block_table;
+  p.kv = c->kv;
+  p.lnf_g = c->lm_lnf.g;
+  p.lnf_b = c->lm_lnf.b;
+  p.sync = m.d_sync;
+  p.sc_cap = (c->max_pages_per_row + 3) & ~3;
+  p.trace = m.trace;
+  p.log2_page_tokens = 0;
+  while ((1 << p.log2_page_tokens) < c->kv.page_tokens) ++p.log2_page_tokens;
+  RUN(mega_launch(p, s));
+  return 0;
+}
+
 int lm_decode_step(ccb_ctx* c, int rows, cudaStream_t s) {
   const ccb_model_desc& D = c->desc;
   const int d = D.lm_d, H = D.lm_heads, hd = d / H;
+  if (c->mega.available && rows <= c->mega.max_rows && c->mega.enabled && (c->kv.page_tokens & (c->kv.page_tokens - 1)) == 0) {
+    if (lm_decode_layers_mega(c, rows, s)) return -1;
+    RUN(linear(c, c->x, d, rows, c->lm_head, CCB_ACT_NONE, nullptr, 0, c->logits, c->ldv, 0, s));
+    return 0;
+  }
   RUN(embed_tokens(c->wte, D.lm_arch == CCB_LM_GPT2 ? c->wpe : nullptr, c->next_tokens, c->ctx_len, c->h, rows, d, s));
   const BlockShape sh = lm_shape(D);
   const float scale = 1.0f / sqrtf(static_cast<float>(hd));
@@ -413,10 +469,10 @@ int decode_iteration(ccb_ctx* c, const ccb_gen_params* p, int N, int rows, int T
   return select_step(c, p, rows, T, false, s);
 }
 
-std::string graph_key(const ccb_gen_params* p, int N, int rows, int T) {
+std::string graph_key(const ccb_gen_params* p, int N, int rows, int T, int c_mega) {
   char buf[512];
-  snprintf(buf, sizeof(buf), "m%d N%d r%d T%d st%d ms%d eos%d t%a p%a k%d rp%a b%d seed%llu q%p ld%lld ids%p pr%p kr%p",
-           p->mode, N, rows, T, p->stop_token, p->max_stops, p->eos_token, p->temperature, p->top_p, p->top_k,
+  snprintf(buf, sizeof(buf), "g%d m%d N%d r%d T%d st%d ms%d eos%d t%a p%a k%d rp%a b%d seed%llu q%p ld%lld ids%p pr%p kr%p",
+           c_mega, p->mode, N, rows, T, p->stop_token, p->max_stops, p->eos_token, p->temperature, p->top_p, p->top_k,
            p->repetition_penalty, p->beam_size, static_cast<unsigned long long>(p->seed),
            static_cast<const void*>(p->q_noise), static_cast<long long>(p->q_ld), static_cast<const void*>(p->row_ids),
            static_cast<const void*>(p->top_p_rows), static_cast<const void*>(p->top_k_rows));
@@ -468,7 +524,7 @@ int generate_on_work_stream(ccb_ctx* c, const ccb_gen_params* p, const float* em
 
   // ---- decode: T-1 replays of one captured step (every kernel reads step / ctx_len from device memory)
   if (T > 1) {
-    const std::string key = graph_key(p, N, rows, T);
+    const std::string key = graph_key(p, N, rows, T, c->mega.enabled ? 1 : 0);
     auto it = c->graphs.find(key);
     if (it == c->graphs.end()) {
       cudaGraph_t graph = nullptr;
@@ -780,6 +836,22 @@ int ccb_create(ccb_ctx** out, const ccb_model_desc* desc, int device) {
   c->has_stopped = a.arr<uint8_t>(c->max_rows);
   c->bos_token = a.arr<int>(D.max_images);
 
+  // ---- persistent decode kernel: GPT-2 blocks with head_dim 64 (every GPT-2 size), up to 256 rows per step
+  MegaState& mg = c->mega;
+  if (D.lm_arch == CCB_LM_GPT2 && lm_hd == 64 && d <= 4096 && mega_init() == 0) {
+    mega_plan(mg, d, 4 * d, c->num_sms);
+    if (mg.tbl_entries <= 512) {
+      mg.max_rows = std::min(c->max_rows, 256);
+      mg.d_wmaps = static_cast<CUtensorMap*>(a.take(sizeof(CUtensorMap) * 4 * D.lm_layers));
+      mg.d_layers = a.arr<MegaLayer>(D.lm_layers);
+      mg.d_tbl = a.arr<uint32_t>(mg.tbl_entries);
+      mg.d_ws = a.arr<float>(mg.ws_floats_per_row * mg.max_rows);
+      mg.d_sync = a.arr<unsigned int>(64);
+      mg.available = true;
+      mg.enabled = mega_enabled();
+    }
+  }
+
   if (!a.ok) {
     fail(nullptr, "ccb_create: out of device memory after %lld bytes", static_cast<long long>(c->device_bytes));
     ccb_destroy(c);
@@ -787,6 +859,27 @@ int ccb_create(ccb_ctx** out, const ccb_model_desc* desc, int device) {
   }
   // zero everything once (optional biases, semaphores, block tables)
   for (size_t i = 0; i < c->allocs.size(); ++i) cudaMemset(c->allocs[i], 0, c->alloc_sizes[i]);
+  if (mg.available) {
+    // weight tensor maps (addresses are fixed from here on; the values arrive through ccb_load_weight)
+    std::vector<CUtensorMap> maps(static_cast<size_t>(4) * D.lm_layers);
+    std::vector<MegaLayer> lys(D.lm_layers);
+    bool ok = true;
+    for (int l = 0; l < D.lm_layers && ok; ++l) {
+      const Block& b = c->lm[l];
+      const Linear* lin[4] = {&b.qkv, &b.proj, &b.fc, &b.fc2};
+      for (int k = 0; k < 4; ++k)
+        ok = ok && gemm_make_tmap(&maps[l * 4 + k], lin[k]->w, lin[k]->features, lin[k]->K, lin[k]->K, 128) == 0;
+      lys[l] = MegaLayer{b.ln1.g, b.ln1.b, b.ln2.g, b.ln2.b, b.qkv.bias, b.proj.bias, b.fc.bias, b.fc2.bias};
+    }
+    ok = ok && cudaMemcpy(mg.d_wmaps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice) == cudaSuccess;
+    ok = ok && cudaMemcpy(mg.d_layers, lys.data(), lys.size() * sizeof(MegaLayer), cudaMemcpyHostToDevice) == cudaSuccess;
+    ok = ok && cudaMemcpy(mg.d_tbl, mg.h_tbl.data(), mg.h_tbl.size() * sizeof(uint32_t), cudaMemcpyHostToDevice) == cudaSuccess;
+    if (!ok) {
+      fail(nullptr, "ccb_create: persistent decode kernel setup failed: %s", gemm_last_error());
+      ccb_destroy(c);
+      return -1;
+    }
+  }
   if (cudaStreamCreateWithFlags(&c->work, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming) != cudaSuccess ||
@@ -1019,6 +1112,34 @@ int ccb_debug_gemm_trace(ccb_ctx* c, void* trace_u64, int64_t stride_u64, int la
   c->gemm_ws.trace_launches = launches > 0 ? launches : 1;
   c->gemm_ws.trace_count = 0;
   return 0;
+}
+
+int ccb_debug_set_mega(ccb_ctx* c, int enable) {
+  if (!c) return -1;
+  c->mega.enabled = enable != 0;
+  return c->mega.available ? 1 : 0;
+}
+
+int ccb_debug_copy_buffer(ccb_ctx* c, int which, void* dst, int64_t bytes, void* stream) {
+  if (!c || !dst) return -1;
+  const void* src = nullptr;
+  switch (which) {
+    case 0: src = c->h; break;
+    case 1: src = c->x; break;
+    case 2: src = c->att; break;
+    case 3: src = c->mlp; break;
+    case 4: src = c->logits; break;
+    case 5: src = c->qkv; break;
+    default: return fail(c, "ccb_debug_copy_buffer: unknown buffer %d", which);
+  }
+  CUDA_OK(cudaMemcpyAsync(dst, src, static_cast<size_t>(bytes), cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int ccb_debug_mega_trace(ccb_ctx* c, void* trace_u64) {
+  if (!c) return -1;
+  c->mega.trace = static_cast<unsigned long long*>(trace_u64);
+  return c->mega.available ? c->mega.ncta : 0;
 }
 
 int ccb_op_layernorm(ccb_ctx* c, const float* x, const float* gamma, const float* beta, float eps, void* y_bf16,

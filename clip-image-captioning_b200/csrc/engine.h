@@ -10,6 +10,7 @@
 
 #include "../../include/clipcap_b200.h"
 #include "internal.h"
+#include "mega.h"
 
 namespace ccb {
 
@@ -115,6 +116,9 @@ struct ccb_ctx {
   float* seq_lengths = nullptr;   // [max_rows]
   uint8_t* has_stopped = nullptr; // [max_rows]
   int* bos_token = nullptr;       // [max_images] scratch for the BOS embedding gather
+
+  // ---- persistent decode-step kernel (decode_mega.cu); unavailable -> operator-per-kernel decode step
+  ccb::MegaState mega;
 
   // ---- streams / graphs / accounting
   cudaStream_t work = nullptr;

@@ -7,6 +7,7 @@
 
 #include "gemm_sm100.cuh"
 #include "internal.h"
+#include "mega.h"
 
 namespace ccb {
 
@@ -88,6 +89,11 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, di
 }  // namespace
 
 const char* gemm_last_error() { return g_err; }
+
+int gemm_make_tmap(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t K, uint64_t ld, uint32_t box_rows) {
+  if (!g_encode) return fail("gemm_init() was not called");
+  return make_tmap(m, ptr, rows, K, ld, box_rows);
+}
 
 int gemm_init(int device) {
   (void)device;

@@ -156,6 +156,17 @@ CCB_API int ccb_op_linear(ccb_ctx* ctx, const void* x, int64_t lda, int tokens, 
  * trace[(n % launches) * stride_u64 + cta * 8 + k] (entry, setup, first tile landed, MMAs issued, accumulator ready,
  * cluster reduction reached, epilogue done, exit).  NULL (the default) disables it. */
 CCB_API int ccb_debug_gemm_trace(ccb_ctx* ctx, void* trace_u64, int64_t stride_u64, int launches);
+/* tuning aid for the persistent decode-step kernel: when non-NULL every CTA writes globaltimer stamps of its phase
+ * boundaries (grid-barrier waits / arrivals, in program order) to trace[cta * 2 * (8 * lm_layers + 2) + k].
+ * Returns the number of CTAs of that kernel (0 when the model shape is not covered by it). */
+CCB_API int ccb_debug_mega_trace(ccb_ctx* ctx, void* trace_u64);
+/* A/B aid: 0 routes decode steps through the operator-per-kernel chain instead of the persistent kernel (default 1,
+ * or CCB_MEGA=0 in the environment).  Returns 1 when the persistent kernel covers this model shape, else 0. */
+CCB_API int ccb_debug_set_mega(ccb_ctx* ctx, int enable);
+/* test aid: copies the first `bytes` of an internal activation workspace to `dst` (device memory) on `stream`:
+ * 0 residual stream h (f32), 1 LayerNorm output x (bf16), 2 attention output (bf16), 3 MLP hidden (bf16),
+ * 4 logits (f32, row pitch = vocab rounded up to 64), 5 fused qkv (bf16; operator-per-kernel decode only). */
+CCB_API int ccb_debug_copy_buffer(ccb_ctx* ctx, int which, void* dst, int64_t bytes, void* stream);
 /* y = LayerNorm(x) over the last dim: x f32 [rows, d] -> y bf16 [rows, d] */
 CCB_API int ccb_op_layernorm(ccb_ctx* ctx, const float* x, const float* gamma, const float* beta, float eps, void* y_bf16,
                      int rows, int d, void* stream);
