@@ -40,6 +40,7 @@ constexpr int kComputeThreads = 256;
 constexpr int kComputeWarp0 = 4;
 constexpr int kWStage = 128 * 64 * 2;
 constexpr int kTblMax = 512;
+constexpr int kLnSlots = 14;            // split-K slots a LayerNorm thread keeps in flight per column
 constexpr int kVecScratch = 64 * 1024;   // vector-phase scratch = the (idle) X ring: 8 KB per compute warp
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
@@ -113,6 +114,7 @@ struct ComputeCtx {
   uint32_t vs_u32;
   float* strips;         // [8 warps][192] floats: q (scaled), k_new, v_new of the unit a warp works on
   bool attn_prefetched;  // the K/V copies of this warp's first attention unit are already in flight
+  int u_ctx[2], u_page[2];  // cached tokens / this lane's page id of the warp's first two attention units
   unsigned long long* trace;
   int trace_it;
 };
@@ -223,16 +225,19 @@ __device__ __noinline__ void ln_phase(const MegaParams& p, ComputeCtx& cc, int c
         float4 a0 = z4, a1 = z4;
         const int nmax = nsl0 > nsl1 ? nsl0 : nsl1;
 #pragma unroll 1
-        for (int s0 = 0; s0 < nmax; s0 += 8) {
-          float4 w0[8], w1[8];
+        for (int s0 = 0; s0 < nmax; s0 += kLnSlots) {
+          // all slots of both columns in flight at once (c_proj / mlp.c_proj tiles have ~13 contributors on 148 SMs)
+          float4 w0[kLnSlots], w1[kLnSlots];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            w0[j] = (s0 + j < nsl0) ? ldcg_f4(src + (q0 << 2) + (s0 + j) * slot_stride) : z4;
-            w1[j] = (s0 + j < nsl1) ? ldcg_f4(src + (q1 << 2) + (s0 + j) * slot_stride) : z4;
+          for (int j = 0; j < kLnSlots; ++j) w0[j] = (s0 + j < nsl0) ? ldcg_f4(src + (q0 << 2) + (s0 + j) * slot_stride) : z4;
+#pragma unroll
+          for (int j = 0; j < kLnSlots; ++j) w1[j] = (s0 + j < nsl1) ? ldcg_f4(src + (q1 << 2) + (s0 + j) * slot_stride) : z4;
+#pragma unroll
+          for (int j = 0; j < kLnSlots; ++j) {
+            a0.x += w0[j].x; a0.y += w0[j].y; a0.z += w0[j].z; a0.w += w0[j].w;
           }
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            a0.x += w0[j].x; a0.y += w0[j].y; a0.z += w0[j].z; a0.w += w0[j].w;
+          for (int j = 0; j < kLnSlots; ++j) {
             a1.x += w1[j].x; a1.y += w1[j].y; a1.z += w1[j].z; a1.w += w1[j].w;
           }
         }
@@ -341,15 +346,24 @@ __device__ __noinline__ void attention_phase(const MegaParams& p, ComputeCtx& cc
   const size_t kv_stride = static_cast<size_t>(cache.num_pages) * page_stride;
   const bf16* layer_k = cache.base + static_cast<size_t>(layer) * 2 * kv_stride;
   const uint32_t lane_dst = static_cast<uint32_t>(grp) * 128u + static_cast<uint32_t>(ch) * 16u;
+  // Context length and page ids do not change during the step: those of a warp's first two units were loaded once at
+  // kernel start (cc.u_ctx / cc.u_page); further units (more than 2 * 8 * ncta units) request theirs one unit ahead.
+  const int maxp = cache.max_pages_per_row;
+  int ctx_nx = 0, page_nx = 0, ui = 0;
 #pragma unroll 1
-  for (int unit = cw * ncta + cta; unit < total; unit += 8 * ncta) {
+  for (int unit = cw * ncta + cta; unit < total; unit += 8 * ncta, ++ui) {
     const int b = unit / H, h = unit - b * H;
-    const int ctx = ctx_len[b];
-    const int* bt = block_table + static_cast<uint32_t>(b) * cache.max_pages_per_row;
+    const int ctx = ui < 2 ? cc.u_ctx[ui] : ctx_nx;
+    const int my_page = ui < 2 ? cc.u_page[ui] : page_nx;
+    const int* bt = block_table + static_cast<uint32_t>(b) * maxp;
+    if (!prefetch_only && ui >= 1 && unit + 8 * ncta < total) {
+      const int bn = (unit + 8 * ncta) / H;
+      ctx_nx = ctx_len[bn];
+      page_nx = lane < maxp ? block_table[static_cast<uint32_t>(bn) * maxp + lane] : 0;
+    }
     const int npages = (ctx >> lpt) + 1;  // pages holding positions [0, ctx]
-    // page ids: one coalesced load when they fit a warp (always for 16-token pages), else per-token lookups
+    // page ids: held one per lane when they fit a warp (always for 16-token pages), else per-token lookups
     const bool pages_in_warp = npages <= 32;
-    const int my_page = (pages_in_warp && lane < npages) ? bt[lane] : 0;
     const bf16* kbase = layer_k + (static_cast<uint32_t>(h) << (lpt + 6)) + ch * 8;  // + page * page_stride + (t & ptm) * 64
     const int nb = (ctx + 15) >> 4;
 
@@ -789,6 +803,17 @@ __global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const __grid_c
     cc.attn_prefetched = false;
     cc.trace = p.trace ? p.trace + static_cast<size_t>(cta) * (2 * (8 * p.L + 2)) : nullptr;
     cc.trace_it = 0;
+#pragma unroll
+    for (int ui = 0; ui < 2; ++ui) {
+      const int unit = (cc.cw + 8 * ui) * ncta + cta;
+      cc.u_ctx[ui] = 0;
+      cc.u_page[ui] = 0;
+      if (unit < p.R * p.H) {
+        const int b = unit / p.H;
+        cc.u_ctx[ui] = p.ctx_len[b];
+        cc.u_page[ui] = lane < p.kv.max_pages_per_row ? p.block_table[static_cast<uint32_t>(b) * p.kv.max_pages_per_row + lane] : 0;
+      }
+    }
     EpiCtx ec;
     ec.tmem_base = tmem_base;
     ec.t_full0 = t_full0;
@@ -804,7 +829,8 @@ __global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const __grid_c
       epilogue_phase(p, cc, ec, cta, 0, l);
       if (sched[0].n == 0) grid_wait(cc, 8 * l + 1);  // (see grid_arrive: no arrival at #k+1 before #k is complete)
       grid_arrive(cc, 0);       // #8l+1
-      if ((p.debug & 4) == 0) attention_phase(p, cc, cta, l, ly.b_qkv, true);
+      // (warp 0 polls the barrier for the CTA: it goes straight to the wait and fetches its K/V afterwards)
+      if ((p.debug & 4) == 0 && cc.cw != 0) attention_phase(p, cc, cta, l, ly.b_qkv, true);
       grid_wait(cc, 8 * l + 2);
       attention_phase(p, cc, cta, l, ly.b_qkv, false);
       grid_arrive(cc, xgo);     // #8l+2

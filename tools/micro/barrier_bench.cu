@@ -1,0 +1,112 @@
+// Microbenchmark: latency of grid-barrier variants for a persistent 148-CTA kernel (256 "compute" threads per CTA).
+// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o barrier_bench barrier_bench.cu
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) { unsigned v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ unsigned ld_relaxed(const unsigned* p) { unsigned v; asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ unsigned ld_volatile(const unsigned* p) { unsigned v; asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void red_release(unsigned* p, unsigned v) { asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void red_relaxed(unsigned* p, unsigned v) { asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void st_release(unsigned* p, unsigned v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void fence_acq_rel() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+
+// every barrier: each thread first writes one float to `data` (so the release has something to publish), the
+// consumer side reads a value another CTA wrote (checks correctness of the ordering)
+template <int V>
+__global__ void __launch_bounds__(256, 1) bar_kernel(unsigned* ctr, unsigned* flags, float* data, int iters, unsigned* errors) {
+  const int cta = blockIdx.x, n = gridDim.x, t = threadIdx.x;
+  unsigned bad = 0;
+  for (int it = 1; it <= iters; ++it) {
+    data[(size_t)cta * 256 + t] = (float)(it * 7 + cta);
+    if (V == 0) {         // named barrier; t0 red.release; t0 polls ld.acquire; named barrier
+      __syncthreads();
+      if (t == 0) { red_release(ctr, 1); while (ld_acquire(ctr) < (unsigned)it * n) {} }
+      __syncthreads();
+    } else if (V == 1) {  // relaxed polling + one acquire fence
+      __syncthreads();
+      if (t == 0) { red_release(ctr, 1); while (ld_relaxed(ctr) < (unsigned)it * n) {} fence_acq_rel(); }
+      __syncthreads();
+    } else if (V == 2) {  // explicit fence + relaxed red, relaxed polling + fence
+      __syncthreads();
+      if (t == 0) { fence_acq_rel(); red_relaxed(ctr, 1); while (ld_relaxed(ctr) < (unsigned)it * n) {} fence_acq_rel(); }
+      __syncthreads();
+    } else if (V == 3) {  // lane 0 of every warp polls (no second CTA barrier)
+      __syncthreads();
+      if (t == 0) red_release(ctr, 1);
+      if ((t & 31) == 0) { while (ld_acquire(ctr) < (unsigned)it * n) {} }
+      __syncwarp();
+    } else if (V == 4) {  // per-CTA flags: st.release own flag; one warp reads all flags
+      __syncthreads();
+      if (t == 0) st_release(flags + cta * 32, (unsigned)it);   // flags 128 B apart
+      if (t < 32) {
+        bool done;
+        do {
+          done = true;
+          for (int c = t; c < n; c += 32) done &= ld_acquire(flags + c * 32) >= (unsigned)it;
+          done = __all_sync(0xffffffffu, done);
+        } while (!done);
+      }
+      __syncthreads();
+    } else if (V == 5) {  // volatile polling (L2), threadfence on both sides
+      __syncthreads();
+      if (t == 0) { __threadfence(); atomicAdd(ctr, 1); while (ld_volatile(ctr) < (unsigned)it * n) {} __threadfence(); }
+      __syncthreads();
+    } else if (V == 6) {  // 8 counters 128 B apart: warp w's lane 0 arrives on and polls counter w
+      __syncthreads();
+      if ((t & 31) == 0) { unsigned* c = ctr + (t >> 5) * 32; red_release(c, 1); while (ld_acquire(c) < (unsigned)it * n) {} }
+      __syncwarp();
+    }
+    // check: read what CTA (cta+1)%n wrote this iteration (through L2)
+    float v;
+    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(data + (size_t)((cta + 1) % n) * 256 + t));
+    if (v != (float)(it * 7 + (cta + 1) % n)) ++bad;
+    // second barrier-free phase separation is not needed: the next iteration's write targets this CTA's own slots,
+    // which the neighbour reads only after the next barrier... it may still be reading this iteration's value:
+    __syncthreads();
+    if (V != 4) { if (t == 0) { red_release(ctr + 1024, 1); while (ld_acquire(ctr + 1024) < (unsigned)it * n) {} } }
+    else { if (t == 0) { red_release(ctr + 1024, 1); while (ld_acquire(ctr + 1024) < (unsigned)it * n) {} } }
+    __syncthreads();
+  }
+  if (bad) atomicAdd(errors, bad);
+}
+
+template <int V>
+float run(unsigned* ctr, unsigned* flags, float* data, unsigned* err, int iters) {
+  cudaMemset(ctr, 0, 8192 * 4);
+  cudaMemset(flags, 0, 148 * 32 * 4);
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  void* args[] = {&ctr, &flags, &data, &iters, &err};
+  cudaEventRecord(e0);
+  cudaLaunchCooperativeKernel((void*)bar_kernel<V>, dim3(148), dim3(256), args, 0, 0);
+  cudaEventRecord(e1);
+  cudaEventSynchronize(e1);
+  float ms; cudaEventElapsedTime(&ms, e0, e1);
+  return ms;
+}
+
+int main() {
+  unsigned *ctr, *flags, *err; float* data;
+  cudaMalloc(&ctr, 8192 * 4); cudaMalloc(&flags, 148 * 32 * 4); cudaMalloc(&data, 148 * 256 * 4); cudaMalloc(&err, 4);
+  cudaMemset(err, 0, 4);
+  const int iters = 2000;
+  // baseline: the fixed second barrier (variant 0 style) costs the same in every variant; report total per iteration
+  float t[7];
+  run<0>(ctr, flags, data, err, 100);
+  t[0] = run<0>(ctr, flags, data, err, iters);
+  t[1] = run<1>(ctr, flags, data, err, iters);
+  t[2] = run<2>(ctr, flags, data, err, iters);
+  t[3] = run<3>(ctr, flags, data, err, iters);
+  t[4] = run<4>(ctr, flags, data, err, iters);
+  t[5] = run<5>(ctr, flags, data, err, iters);
+  t[6] = run<6>(ctr, flags, data, err, iters);
+  unsigned herr; cudaMemcpy(&herr, err, 4, cudaMemcpyDeviceToHost);
+  const char* names[7] = {"t0 red.release + ld.acquire poll", "relaxed poll + fence", "fence + red.relaxed, relaxed poll + fence",
+                          "8 pollers (lane 0 per warp)", "per-CTA flags, one warp reads all", "threadfence + atomicAdd + volatile poll", "8 counters, per-warp"};
+  // every iteration = variant barrier + one V0-style barrier: V0 total / 2 = cost of one V0 barrier
+  const float v0 = t[0] / iters / 2 * 1000;
+  for (int i = 0; i < 7; ++i) printf("variant %d (%s): %.3f us per barrier\n", i, names[i], t[i] / iters * 1000 - v0);
+  printf("ordering errors: %u (%s)\n", herr, cudaGetErrorString(cudaGetLastError()));
+  return 0;
+}
