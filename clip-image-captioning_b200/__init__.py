@@ -7,9 +7,9 @@ creating an `Engine` does, and there is no CPU fallback.
 from . import _lib
 from ._lib import GenParams, ModelDesc
 from .engine import Engine, EngineConfig
-from . import evaluate_model, inference, lms, model, sampling, synthetic
+from . import evaluate_model, inference, lms, model, sampling, sharding, synthetic
 from .lms import GPT2, GPTJ, IdTokenizer
 from .model import CLIPCaptionModel, CLIPCaptionPrefixOnly
 
 __all__ = ["Engine", "EngineConfig", "GenParams", "ModelDesc", "CLIPCaptionModel", "CLIPCaptionPrefixOnly", "GPT2", "GPTJ",
-           "IdTokenizer", "inference", "evaluate_model", "sampling", "synthetic", "lms", "model", "_lib"]
+           "IdTokenizer", "inference", "evaluate_model", "sampling", "sharding", "synthetic", "lms", "model", "_lib"]

@@ -14,9 +14,15 @@ synthetic.load_synthetic(eng)
 torch.cuda.empty_cache()
 images = synthetic.synthetic_images(B, cfg, device="cuda")
 p = eng.gen_params("greedy", T, stop_token=-1, max_stops=0)
+profile_last = os.environ.get("CCB_PROFILE_LAST") == "1"   # with: ncu --profile-from-start off
 for it in range(iters):
+    if profile_last and it == iters - 1:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
     tokens, lengths, scores = eng.caption_images(images, p)
     torch.cuda.synchronize()
     pre, dec, steps = eng.last_timing()
     print("iter %d: prefill %.2f ms decode %.3f ms/step" % (it, pre, dec / max(steps, 1)))
+if profile_last:
+    torch.cuda.profiler.stop()
 print(tokens[0].tolist())
