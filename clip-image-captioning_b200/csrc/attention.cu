@@ -5,6 +5,8 @@
 //    it also writes K/V into the paged cache.
 //  * attention_decode: one query token per row against the paged KV cache; memory-bound, 16-byte loads,
 //    online softmax, 4 warps per (row, head) each striding over the context, merged through shared memory.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "internal.h"
 #include "ptx.cuh"
@@ -135,6 +137,211 @@ __global__ void __launch_bounds__(kPrefillWarps * 32) attention_prefill_kernel(
     }
     __syncwarp();
   }
+}
+
+// ------------------------------------------------------------------------------------------------ prefill, tensor cores
+// Same operator for S <= 128, head_dim % 8 == 0, head_dim <= 256, no rotary: one CTA per (batch, head), one warp per
+// 16 query rows, mma.sync m16n8k16 (bf16 in, fp32 accumulate) for Q K^T and P V.  K and V of the head are staged once
+// in shared memory (row pitch head_dim rounded to 16, + 8 elements: conflict-free fragment loads and 16-byte aligned
+// ldmatrix rows); the scores of a query tile stay in registers from Q K^T through the softmax into the P operand.  The scalar kernel above spent
+// ~4000 instructions per warp on this (88 us per GPT2-XL layer at batch 64); this one is a few hundred.
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldmatrix_x2_trans(uint32_t& r0, uint32_t& r1, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+
+template <int NT, int KS>   // NT: key tiles of 8 (even, >= 2 * warps); KS: head_dim steps of 16
+__global__ void __launch_bounds__(256) attention_prefill_mma_kernel(
+    const bf16* __restrict__ qkv, bf16* __restrict__ out, int S, int H, int hd, float scale, int causal,
+    KvCache cache, int layer, const int* __restrict__ block_table, int pos0, int write_cache,
+    const uint8_t* __restrict__ key_mask) {
+  extern __shared__ uint4 smem_u4[];
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int d = H * hd;
+  const int HDP = KS * 16 + 8;            // row pitch in elements
+  const int S16 = NT * 8;                 // staged key rows
+  bf16* Ks = reinterpret_cast<bf16*>(smem_u4);
+  bf16* Vs = Ks + S16 * HDP;
+  float* mask_add = reinterpret_cast<float*>(Vs + S16 * HDP);   // 0 or -inf per key
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const bf16* base = qkv + static_cast<size_t>(b) * S * 3 * d;
+
+  // ---- stage K / V (16-byte chunks, zero padded), append them to the KV cache, build the key mask
+  const int cpr = HDP / 8;                // chunks per staged row
+  for (int idx = threadIdx.x; idx < S16 * cpr; idx += blockDim.x) {
+    const int j = idx / cpr, c = idx - j * cpr;
+    uint4 kk = make_uint4(0u, 0u, 0u, 0u), vv = kk;
+    if (j < S && c * 8 < hd) {
+      const bf16* rowp = base + static_cast<size_t>(j) * 3 * d + h * hd + c * 8;
+      kk = *reinterpret_cast<const uint4*>(rowp + d);
+      vv = *reinterpret_cast<const uint4*>(rowp + 2 * d);
+      if (write_cache) {
+        const int pos = pos0 + j;
+        const int page = block_table[static_cast<size_t>(b) * cache.max_pages_per_row + pos / cache.page_tokens];
+        const int tin = pos % cache.page_tokens;
+        *reinterpret_cast<uint4*>(cache.base + kv_index(cache, layer, 0, page, h, tin) + c * 8) = kk;
+        *reinterpret_cast<uint4*>(cache.base + kv_index(cache, layer, 1, page, h, tin) + c * 8) = vv;
+      }
+    }
+    *reinterpret_cast<uint4*>(Ks + j * HDP + c * 8) = kk;
+    *reinterpret_cast<uint4*>(Vs + j * HDP + c * 8) = vv;
+  }
+  for (int j = threadIdx.x; j < S16; j += blockDim.x)
+    mask_add[j] = (j < S && (key_mask == nullptr || key_mask[static_cast<size_t>(b) * S + j])) ? 0.f : -INFINITY;
+  __syncthreads();
+
+  const int r0 = warp * 16;               // this warp's query rows r0 + g, r0 + g + 8
+  if (r0 >= S) return;
+  const int row_a = r0 + g, row_b = r0 + g + 8;
+
+  // ---- Q fragments straight from global memory (A operand, row-major)
+  uint32_t qf[KS][4];
+  {
+    const bf16* qa = base + static_cast<size_t>(row_a) * 3 * d + h * hd;
+    const bf16* qb = base + static_cast<size_t>(row_b) * 3 * d + h * hd;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      const int k0 = ks * 16 + 2 * t, k1 = k0 + 8;
+      qf[ks][0] = (row_a < S && k0 < hd) ? *reinterpret_cast<const uint32_t*>(qa + k0) : 0u;
+      qf[ks][1] = (row_b < S && k0 < hd) ? *reinterpret_cast<const uint32_t*>(qb + k0) : 0u;
+      qf[ks][2] = (row_a < S && k1 < hd) ? *reinterpret_cast<const uint32_t*>(qa + k1) : 0u;
+      qf[ks][3] = (row_b < S && k1 < hd) ? *reinterpret_cast<const uint32_t*>(qb + k1) : 0u;
+    }
+  }
+  // ---- scores = Q K^T
+  float sc[NT][4];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+    const bf16* krow = Ks + (nt * 8 + g) * HDP + 2 * t;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      const uint32_t b0 = *reinterpret_cast<const uint32_t*>(krow + ks * 16);
+      const uint32_t b1 = *reinterpret_cast<const uint32_t*>(krow + ks * 16 + 8);
+      mma_bf16_16816(sc[nt], qf[ks], b0, b1);
+    }
+  }
+  // ---- mask, softmax over the row (thread holds keys nt*8 + 2t, +1 of rows a and b; the 4 lanes of a quad share a row)
+  float mx_a = -INFINITY, mx_b = -INFINITY;
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int key = nt * 8 + 2 * t + e;
+      const float m = mask_add[key];
+      const float va = (causal && key > row_a) ? -INFINITY : sc[nt][e] * scale + m;
+      const float vb = (causal && key > row_b) ? -INFINITY : sc[nt][2 + e] * scale + m;
+      sc[nt][e] = va;
+      sc[nt][2 + e] = vb;
+      mx_a = fmaxf(mx_a, va);
+      mx_b = fmaxf(mx_b, vb);
+    }
+  }
+  mx_a = fmaxf(mx_a, __shfl_xor_sync(0xffffffffu, mx_a, 1));
+  mx_a = fmaxf(mx_a, __shfl_xor_sync(0xffffffffu, mx_a, 2));
+  mx_b = fmaxf(mx_b, __shfl_xor_sync(0xffffffffu, mx_b, 1));
+  mx_b = fmaxf(mx_b, __shfl_xor_sync(0xffffffffu, mx_b, 2));
+  float sum_a = 0.f, sum_b = 0.f;
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const float pa = (sc[nt][e] == -INFINITY) ? 0.f : expf(sc[nt][e] - mx_a);
+      const float pb = (sc[nt][2 + e] == -INFINITY) ? 0.f : expf(sc[nt][2 + e] - mx_b);
+      sc[nt][e] = pa;
+      sc[nt][2 + e] = pb;
+      sum_a += pa;
+      sum_b += pb;
+    }
+  }
+  sum_a += __shfl_xor_sync(0xffffffffu, sum_a, 1);
+  sum_a += __shfl_xor_sync(0xffffffffu, sum_a, 2);
+  sum_b += __shfl_xor_sync(0xffffffffu, sum_b, 1);
+  sum_b += __shfl_xor_sync(0xffffffffu, sum_b, 2);
+  const float inv_a = sum_a > 0.f ? 1.f / sum_a : 0.f, inv_b = sum_b > 0.f ? 1.f / sum_b : 0.f;
+  // ---- P as the A operand of the second product (keys are its k dimension: tile pair (2kk, 2kk+1) = 16 keys).
+  // P is split into two bf16 terms (p = hi + lo, |lo| <= 2^-9 |p|) and multiplied in two MMAs, so the probabilities
+  // keep ~16 significant bits: the result stays within fp32-accumulation noise of the fp32-softmax formulation and
+  // greedy captions on near-tie logits do not depend on the kernel choice.
+  uint32_t pf[NT / 2][4], pl[NT / 2][4];
+#pragma unroll
+  for (int kk = 0; kk < NT / 2; ++kk) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int nt = 2 * kk + (q >> 1), e = (q & 1) * 2;   // q: 0 -> (tile 2kk, row a), 1 -> (2kk, row b), 2 -> (2kk+1, a), 3 -> (2kk+1, b)
+      const float inv = (q & 1) ? inv_b : inv_a;
+      const float x0 = sc[nt][e] * inv, x1 = sc[nt][e + 1] * inv;
+      const uint32_t hi = pack_bf16x2(x0, x1);
+      const float2 hf = unpack_bf16x2(hi);
+      pf[kk][q] = hi;
+      pl[kk][q] = pack_bf16x2(x0 - hf.x, x1 - hf.y);
+    }
+  }
+  // ---- O = P V, 64 output dims at a time
+  const uint32_t vs_u32 = ptx::smem_u32(Vs);
+  bf16* oa = out + (static_cast<size_t>(b) * S + row_a) * d + h * hd;
+  bf16* ob = out + (static_cast<size_t>(b) * S + row_b) * d + h * hd;
+#pragma unroll 1
+  for (int dc = 0; dc < hd; dc += 64) {
+    float o[8][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < NT / 2; ++kk) {
+      // lanes 0..15 address the 16 key rows of this k step (lanes 16..31 repeat them: ignored by .x2)
+      const uint32_t vrow = vs_u32 + static_cast<uint32_t>(((kk * 16 + (lane & 15)) * HDP + dc) * 2);
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        if (dc + n * 8 < hd) {   // (warp-uniform)
+          uint32_t b0, b1;
+          ldmatrix_x2_trans(b0, b1, vrow + n * 16);
+          mma_bf16_16816(o[n], pf[kk], b0, b1);
+          mma_bf16_16816(o[n], pl[kk], b0, b1);
+        }
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      const int dim = dc + n * 8 + 2 * t;
+      if (dim < hd) {
+        if (row_a < S) *reinterpret_cast<uint32_t*>(oa + dim) = pack_bf16x2(o[n][0], o[n][1]);
+        if (row_b < S) *reinterpret_cast<uint32_t*>(ob + dim) = pack_bf16x2(o[n][2], o[n][3]);
+      }
+    }
+  }
+}
+
+template <int NT, int KS>
+int launch_prefill_mma(const bf16* qkv, bf16* out, int B, int S, int H, int hd, float scale, int causal, const KvCache& c,
+                       int layer, const int* block_table, int pos0, int write_cache, const uint8_t* key_mask, cudaStream_t s) {
+  const int HDP = KS * 16 + 8, S16 = NT * 8;
+  const size_t smem = static_cast<size_t>(2) * S16 * HDP * sizeof(bf16) + S16 * sizeof(float);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(attention_prefill_mma_kernel<NT, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return (int)e;
+    configured = smem;
+  }
+  const int warps = (S + 15) / 16;
+  attention_prefill_mma_kernel<NT, KS><<<dim3(H, B), warps * 32, smem, s>>>(qkv, out, S, H, hd, scale, causal, c, layer,
+                                                                           block_table, pos0, write_cache, key_mask);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
+template <int NT>
+int dispatch_prefill_mma_ks(int ks, const bf16* qkv, bf16* out, int B, int S, int H, int hd, float scale, int causal,
+                            const KvCache& c, int layer, const int* bt, int pos0, int wc, const uint8_t* km, cudaStream_t s) {
+  if (ks <= 4) return launch_prefill_mma<NT, 4>(qkv, out, B, S, H, hd, scale, causal, c, layer, bt, pos0, wc, km, s);
+  if (ks <= 8) return launch_prefill_mma<NT, 8>(qkv, out, B, S, H, hd, scale, causal, c, layer, bt, pos0, wc, km, s);
+  if (ks <= 13) return launch_prefill_mma<NT, 13>(qkv, out, B, S, H, hd, scale, causal, c, layer, bt, pos0, wc, km, s);
+  return launch_prefill_mma<NT, 16>(qkv, out, B, S, H, hd, scale, causal, c, layer, bt, pos0, wc, km, s);
 }
 
 // ------------------------------------------------------------------------------------------------ decode
@@ -282,6 +489,21 @@ int attention_prefill(const bf16* qkv, bf16* out, int B, int S, int H, int hd, f
                       const uint8_t* key_mask, cudaStream_t s) {
   if (B <= 0 || S <= 0) return 0;
   if (S > 256 || hd % 2) return (int)cudaErrorInvalidValue;
+  static const bool use_mma = [] {
+    const char* e = getenv("CCB_ATTN_MMA");
+    return !(e && e[0] == '0');
+  }();
+  if (use_mma && S <= 128 && hd % 8 == 0 && hd <= 256 && rotary_dim == 0) {
+    KvCache c;
+    if (cache) c = *cache;
+    const int wc = cache != nullptr ? 1 : 0;
+    const int ks = (hd + 15) / 16, nt = 2 * ((S + 15) / 16);
+    if (nt <= 4) return dispatch_prefill_mma_ks<4>(ks, qkv, out, B, S, H, hd, scale, causal, c, layer, block_table, pos0, wc, key_mask, s);
+    if (nt <= 6) return dispatch_prefill_mma_ks<6>(ks, qkv, out, B, S, H, hd, scale, causal, c, layer, block_table, pos0, wc, key_mask, s);
+    if (nt <= 8) return dispatch_prefill_mma_ks<8>(ks, qkv, out, B, S, H, hd, scale, causal, c, layer, block_table, pos0, wc, key_mask, s);
+    if (nt <= 10) return dispatch_prefill_mma_ks<10>(ks, qkv, out, B, S, H, hd, scale, causal, c, layer, block_table, pos0, wc, key_mask, s);
+    return dispatch_prefill_mma_ks<16>(ks, qkv, out, B, S, H, hd, scale, causal, c, layer, block_table, pos0, wc, key_mask, s);
+  }
   const size_t smem = (static_cast<size_t>(S) * (hd / 2 + 1) + static_cast<size_t>(S) * (hd / 2) + 1) * 4 +
                       static_cast<size_t>(kPrefillWarps) * (hd + S) * 4;
   if (smem > 200 * 1024) return (int)cudaErrorInvalidValue;
