@@ -41,7 +41,8 @@ constexpr int kComputeWarp0 = 4;
 constexpr int kWStage = 128 * 64 * 2;
 constexpr int kTblMax = 512;
 constexpr int kLnSlots = 14;            // split-K slots a LayerNorm thread keeps in flight per column
-constexpr int kVecScratch = 64 * 1024;   // vector-phase scratch = the (idle) X ring: 8 KB per compute warp
+constexpr int kAttnWarps = 11;           // the 8 compute warps + the X-producer, MMA and TMEM-allocator warps (idle then)
+constexpr int kVecScratch = kAttnWarps * 8192;  // vector-phase scratch: the (idle) X ring and what follows it, 8 KB per warp
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   unsigned v;
@@ -139,11 +140,12 @@ __device__ __forceinline__ void stamp(ComputeCtx& cc) {
 // The counter is shared by all barriers (barrier #k is complete at (k + 1) * ncta arrivals), so a CTA must never arrive
 // at #k+1 before #k is complete: a CTA with GEMM work gets that from its own data dependence (epilogue <- MMA <- X
 // tiles <- poll of #k), a CTA without units of a GEMM waits explicitly.
-__device__ __forceinline__ void grid_arrive(ComputeCtx& cc, uint32_t xgo_bar) {
+__device__ __forceinline__ void grid_arrive(ComputeCtx& cc, uint32_t xgo_bar, uint32_t helpers_bar = 0, uint32_t helpers_parity = 0) {
   ptx::fence_proxy_async();  // this thread's generic accesses to the X ring (vector scratch) before TMA reuses it
   ptx::named_bar_sync(1, kComputeThreads);
   stamp(cc);
   if (cc.ct == 0) {
+    if (helpers_bar != 0) ptx::mbar_wait(helpers_bar, helpers_parity);  // the helper warps' share of the phase is stored
     fence_proxy_async_all();  // the global writes are read through TMA (async proxy) by other CTAs
     red_release_add(cc.ctr, 1u);
     if (xgo_bar != 0) ptx::mbar_arrive(xgo_bar);  // the X producer may start polling for this barrier
@@ -347,17 +349,17 @@ __device__ __noinline__ void attention_phase(const MegaParams& p, ComputeCtx& cc
   const bf16* layer_k = cache.base + static_cast<size_t>(layer) * 2 * kv_stride;
   const uint32_t lane_dst = static_cast<uint32_t>(grp) * 128u + static_cast<uint32_t>(ch) * 16u;
   // Context length and page ids do not change during the step: those of a warp's first two units were loaded once at
-  // kernel start (cc.u_ctx / cc.u_page); further units (more than 2 * 8 * ncta units) request theirs one unit ahead.
+  // kernel start (cc.u_ctx / cc.u_page); further units (more than 2 * 11 * ncta units) request theirs one unit ahead.
   const int maxp = cache.max_pages_per_row;
   int ctx_nx = 0, page_nx = 0, ui = 0;
 #pragma unroll 1
-  for (int unit = cw * ncta + cta; unit < total; unit += 8 * ncta, ++ui) {
+  for (int unit = cw * ncta + cta; unit < total; unit += kAttnWarps * ncta, ++ui) {
     const int b = unit / H, h = unit - b * H;
     const int ctx = ui < 2 ? cc.u_ctx[ui] : ctx_nx;
     const int my_page = ui < 2 ? cc.u_page[ui] : page_nx;
     const int* bt = block_table + static_cast<uint32_t>(b) * maxp;
-    if (!prefetch_only && ui >= 1 && unit + 8 * ncta < total) {
-      const int bn = (unit + 8 * ncta) / H;
+    if (!prefetch_only && ui >= 1 && unit + kAttnWarps * ncta < total) {
+      const int bn = (unit + kAttnWarps * ncta) / H;
       ctx_nx = ctx_len[bn];
       page_nx = lane < maxp ? block_table[static_cast<uint32_t>(bn) * maxp + lane] : 0;
     }
@@ -519,6 +521,43 @@ __device__ __noinline__ void attention_phase(const MegaParams& p, ComputeCtx& cc
   }
 }
 
+// attention state of a warp: its unit(s) never change during the step, so context length and page ids are read once
+__device__ __forceinline__ void init_attn_ctx(const MegaParams& p, ComputeCtx& cc, int aw, int lane, int cta, const uint32_t* tbl,
+                                              uint8_t* vs, uint32_t vs_u32, float* strips) {
+  cc.cw = aw;
+  cc.lane = lane;
+  cc.tbl = tbl;
+  cc.vs = vs;
+  cc.vs_u32 = vs_u32;
+  cc.strips = strips;
+  cc.attn_prefetched = false;
+#pragma unroll
+  for (int ui = 0; ui < 2; ++ui) {
+    const int unit = (aw + kAttnWarps * ui) * p.ncta + cta;
+    cc.u_ctx[ui] = 0;
+    cc.u_page[ui] = 0;
+    if (unit < p.R * p.H) {
+      const int b = unit / p.H;
+      cc.u_ctx[ui] = p.ctx_len[b];
+      cc.u_page[ui] = lane < p.kv.max_pages_per_row ? p.block_table[static_cast<uint32_t>(b) * p.kv.max_pages_per_row + lane] : 0;
+    }
+  }
+}
+
+// The X-producer, MMA and TMEM-allocator warps have nothing to do while the attention phase runs: each takes the
+// attention units of one more "compute warp" (11 instead of 8 warps: GPT2-XL x 64 rows = 1600 units on 148 x 11 warps,
+// one unit per warp instead of two for a third of them).  Their K/V staging lies behind the X ring, so they prefetch as
+// soon as they get here; vgo = c_attn complete everywhere, vdone = this warp's outputs are stored.
+__device__ __forceinline__ void helper_attention(const MegaParams& p, ComputeCtx& hc, int cta, int l, uint32_t vgo, uint32_t vdone) {
+  const float* bias = p.layers[l].b_qkv;
+  attention_phase(p, hc, cta, l, bias, true);
+  ptx::mbar_wait(vgo, static_cast<uint32_t>(l) & 1u);
+  attention_phase(p, hc, cta, l, bias, false);
+  fence_proxy_async_all();   // att rows are fetched by other CTAs through TMA
+  __syncwarp();
+  if (hc.lane == 0) ptx::mbar_arrive(vdone);
+}
+
 struct EpiCtx {
   uint32_t tmem_base, t_full0, t_empty0;  // barrier b at +8 b
   uint32_t ait;                           // accumulator buffers consumed so far
@@ -613,20 +652,23 @@ __global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const __grid_c
   const uint32_t xstage = static_cast<uint32_t>(p.N) * 128u;
   const uint32_t w_ring = base;
   const uint32_t x_ring = w_ring + nW * kWStage;
-  // after the X ring (>= kVecScratch bytes): q/k/v strips (8 x 192 floats), reduction scratch, schedule, tile table, barriers
+  // after the X ring / vector scratch (>= kVecScratch bytes): q/k/v strips (11 x 192 floats), reduction scratch,
+  // schedule, tile table, barriers
   const uint32_t misc_off = nW * kWStage + p.xring_bytes;
   float* strips = reinterpret_cast<float*>(gen + misc_off);
-  float* red = reinterpret_cast<float*>(gen + misc_off + 8 * 192 * 4);
-  KindSched* sched = reinterpret_cast<KindSched*>(gen + misc_off + 8 * 192 * 4 + 64);
-  uint32_t* tbl = reinterpret_cast<uint32_t*>(gen + misc_off + 8 * 192 * 4 + 64 + 64);
-  const uint32_t bar_off = misc_off + 8 * 192 * 4 + 64 + 64 + kTblMax * 4;
+  float* red = reinterpret_cast<float*>(gen + misc_off + kAttnWarps * 192 * 4);
+  KindSched* sched = reinterpret_cast<KindSched*>(gen + misc_off + kAttnWarps * 192 * 4 + 64);
+  uint32_t* tbl = reinterpret_cast<uint32_t*>(gen + misc_off + kAttnWarps * 192 * 4 + 64 + 64);
+  const uint32_t bar_off = misc_off + kAttnWarps * 192 * 4 + 64 + 64 + kTblMax * 4;
   const uint32_t bars = base + bar_off;
   // barrier layout: w_full[nW], w_empty[nW], x_full[nX], x_empty[nX], t_full[2], t_empty[2], xgo, tmem slot
   const uint32_t w_full0 = bars, w_empty0 = bars + 8u * nW;
   const uint32_t x_full0 = bars + 16u * nW, x_empty0 = x_full0 + 8u * nX;
   const uint32_t t_full0 = x_empty0 + 8u * nX, t_empty0 = t_full0 + 16u;
   const uint32_t xgo = t_empty0 + 16u;  // compute -> X producer: "this CTA arrived at the barrier you need"
-  const uint32_t tmem_slot = xgo + 8u;
+  const uint32_t vgo = xgo + 8u;        // compute -> helper warps: "c_attn is complete everywhere: attention may start"
+  const uint32_t vdone = vgo + 8u;      // helper warps -> compute: "my attention unit of this layer is stored"
+  const uint32_t tmem_slot = vdone + 8u;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -646,6 +688,8 @@ __global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const __grid_c
       ptx::mbar_init(t_empty0 + 8u * b, 8);
     }
     ptx::mbar_init(xgo, 1);
+    ptx::mbar_init(vgo, 1);
+    ptx::mbar_init(vdone, 3);
     ptx::fence_mbar_init();
   }
   if (threadIdx.x >= 32 && threadIdx.x < 36) {
@@ -699,13 +743,18 @@ __global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const __grid_c
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ X producer
-    if (!skip_gemm) {
+    // ------------------------------------------------------------------ X producer (+ attention helper)
+    ComputeCtx hc;
+    init_attn_ctx(p, hc, 8, lane, cta, tbl, gen + nW * kWStage, x_ring, strips);
+    if (skip_gemm) {
+      for (int l = 0; l < p.L; ++l) helper_attention(p, hc, cta, l, vgo, vdone);
+    } else {
       uint32_t s = 0, ph = 0;
 #pragma unroll 1
       for (int l = 0; l < p.L; ++l) {
 #pragma unroll 1
         for (int kind = 0; kind < 4; ++kind) {
+          if (kind == 1) helper_attention(p, hc, cta, l, vgo, vdone);   // between the c_attn and the c_proj tiles
           const CUtensorMap* xm = (kind == 1) ? &xmap_att : (kind == 3) ? &xmap_mlp : &xmap_x;
           const KindSched sc = sched[kind];
           if (sc.n == 0) continue;
@@ -735,8 +784,12 @@ __global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const __grid_c
       }
     }
   } else if (warp == 2) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (!skip_gemm) {
+    // ------------------------------------------------------------------ MMA issuer (+ attention helper)
+    ComputeCtx hc;
+    init_attn_ctx(p, hc, 9, lane, cta, tbl, gen + nW * kWStage, x_ring, strips);
+    if (skip_gemm) {
+      for (int l = 0; l < p.L; ++l) helper_attention(p, hc, cta, l, vgo, vdone);
+    } else {
       const uint32_t idesc = ptx::umma_idesc_bf16(128, p.N);
       const uint64_t wdesc0 = ptx::umma_desc_k_sw128(w_ring), xdesc0 = ptx::umma_desc_k_sw128(x_ring);
       uint32_t ws = 0, wph = 0, xs = 0, xph = 0, ait = 0;
@@ -744,6 +797,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const __grid_c
       for (int l = 0; l < p.L; ++l) {
 #pragma unroll 1
         for (int kind = 0; kind < 4; ++kind) {
+          if (kind == 1) helper_attention(p, hc, cta, l, vgo, vdone);   // all c_attn MMAs of this CTA are issued
           const KindSched sc = sched[kind];
           int n = sc.n, kb = sc.kb0;
 #pragma unroll 1
@@ -785,6 +839,11 @@ __global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const __grid_c
         }
       }
     }
+  } else if (warp == 3) {
+    // ------------------------------------------------------------------ TMEM owner: attention helper only
+    ComputeCtx hc;
+    init_attn_ctx(p, hc, 10, lane, cta, tbl, gen + nW * kWStage, x_ring, strips);
+    for (int l = 0; l < p.L; ++l) helper_attention(p, hc, cta, l, vgo, vdone);
   } else if (warp >= kComputeWarp0) {
     // ------------------------------------------------------------------ compute warps
     ComputeCtx cc;
@@ -800,20 +859,9 @@ __global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const __grid_c
     cc.vs = gen + nW * kWStage;
     cc.vs_u32 = x_ring;
     cc.strips = strips;
-    cc.attn_prefetched = false;
     cc.trace = p.trace ? p.trace + static_cast<size_t>(cta) * (2 * (8 * p.L + 2)) : nullptr;
     cc.trace_it = 0;
-#pragma unroll
-    for (int ui = 0; ui < 2; ++ui) {
-      const int unit = (cc.cw + 8 * ui) * ncta + cta;
-      cc.u_ctx[ui] = 0;
-      cc.u_page[ui] = 0;
-      if (unit < p.R * p.H) {
-        const int b = unit / p.H;
-        cc.u_ctx[ui] = p.ctx_len[b];
-        cc.u_page[ui] = lane < p.kv.max_pages_per_row ? p.block_table[static_cast<uint32_t>(b) * p.kv.max_pages_per_row + lane] : 0;
-      }
-    }
+    init_attn_ctx(p, cc, warp - kComputeWarp0, lane, cta, tbl, gen + nW * kWStage, x_ring, strips);
     EpiCtx ec;
     ec.tmem_base = tmem_base;
     ec.t_full0 = t_full0;
@@ -832,8 +880,9 @@ __global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const __grid_c
       // (warp 0 polls the barrier for the CTA: it goes straight to the wait and fetches its K/V afterwards)
       if ((p.debug & 4) == 0 && cc.cw != 0) attention_phase(p, cc, cta, l, ly.b_qkv, true);
       grid_wait(cc, 8 * l + 2);
+      if (cc.ct == 0) ptx::mbar_arrive(vgo);   // the helper warps start their units
       attention_phase(p, cc, cta, l, ly.b_qkv, false);
-      grid_arrive(cc, xgo);     // #8l+2
+      grid_arrive(cc, xgo, vdone, static_cast<uint32_t>(l) & 1u);     // #8l+2
       epilogue_phase(p, cc, ec, cta, 1, l);
       if (sched[1].n == 0) grid_wait(cc, 8 * l + 3);  // (see grid_arrive: no arrival at #k+1 before #k is complete)
       grid_arrive(cc, 0);       // #8l+3
@@ -917,7 +966,7 @@ int mega_launch(const MegaParams& p_in, cudaStream_t s) {
   // shared memory budget: W ring + X ring (doubles as the vector phases' scratch) + strips / tables / barriers
   const int total = 227 * 1024 - 1024 /*alignment*/;
   const int xstage = p.N * 128;
-  const int fixed = 8 * 192 * 4 + 64 + 64 + kTblMax * 4 + 512;
+  const int fixed = kAttnWarps * 192 * 4 + 64 + 64 + kTblMax * 4 + 512;
   p.nX = p.N <= 64 ? 8 : p.N <= 128 ? 4 : 3;
   p.xring_bytes = p.nX * xstage > kVecScratch ? p.nX * xstage : kVecScratch;
   p.nW = (total - fixed - p.xring_bytes) / kWStage;
