@@ -39,7 +39,7 @@ constexpr int kThreads = 384;
 constexpr int kComputeThreads = 256;
 constexpr int kComputeWarp0 = 4;
 constexpr int kWStage = 128 * 64 * 2;
-constexpr int kTblMax = 512;
+constexpr int kTblMax = 256;
 constexpr int kLnSlots = 14;            // split-K slots a LayerNorm thread keeps in flight per column
 constexpr int kAttnWarps = 11;           // the 8 compute warps + the X-producer, MMA and TMEM-allocator warps (idle then)
 constexpr int kVecScratch = kAttnWarps * 8192;  // vector-phase scratch: the (idle) X ring and what follows it, 8 KB per warp
@@ -719,8 +719,11 @@ __global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const __grid_c
     // ------------------------------------------------------------------ W producer
     // (the whole warp walks the schedule and waits; one elected lane issues: converged code lets the compiler emit
     //  the single-thread instructions without a per-instruction election loop)
+    // Ring slots are handed over in PAIRS (two consecutive units of this CTA's stream share one full / empty barrier):
+    // half the waits, expect_tx and commits per byte in all three role loops, which are what paces a GEMM phase.
     if (!skip_gemm) {
-      uint32_t s = 0, ph = 0;
+      uint32_t sp = 0, ph = 0;   // slot pair, its phase
+      const uint32_t nWp = static_cast<uint32_t>(nW) >> 1;
 #pragma unroll 1
       for (int l = 0; l < p.L; ++l) {
 #pragma unroll 1
@@ -729,15 +732,21 @@ __global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const __grid_c
           const KindSched sc = sched[kind];
           int tile = sc.tile0, kb = sc.kb0;
 #pragma unroll 1
-          for (int n = sc.n; n > 0; --n) {
-            ptx::mbar_wait(w_empty0 + 8u * s, ph ^ 1);
+          for (int n = sc.n; n > 0; n -= 2) {
+            const bool two = n > 1;
+            ptx::mbar_wait(w_empty0 + 8u * sp, ph ^ 1);
             if (ptx::elect_one()) {
-              ptx::mbar_arrive_expect_tx(w_full0 + 8u * s, kWStage);
-              ptx::tma_load_2d(w_ring + s * kWStage, wm, w_full0 + 8u * s, kb * 64, tile * 128, ptx::kEvictFirst);
+              const uint32_t full = w_full0 + 8u * sp;
+              ptx::mbar_arrive_expect_tx(full, two ? 2 * kWStage : kWStage);
+              ptx::tma_load_2d(w_ring + (2 * sp) * kWStage, wm, full, kb * 64, tile * 128, ptx::kEvictFirst);
+              int kb2 = kb + 1, tile2 = tile;
+              if (kb2 == sc.kb) { kb2 = 0; ++tile2; }
+              if (two) ptx::tma_load_2d(w_ring + (2 * sp + 1) * kWStage, wm, full, kb2 * 64, tile2 * 128, ptx::kEvictFirst);
             }
             __syncwarp();
-            if (++s == static_cast<uint32_t>(nW)) { s = 0; ph ^= 1; }
-            if (++kb == sc.kb) { kb = 0; ++tile; }
+            if (++sp == nWp) { sp = 0; ph ^= 1; }
+            kb += 2;
+            while (kb >= sc.kb) { kb -= sc.kb; ++tile; }
           }
         }
       }
@@ -769,15 +778,21 @@ __global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const __grid_c
           __syncwarp();
           int kb = sc.kb0;
 #pragma unroll 1
-          for (int n = sc.n; n > 0; --n) {
+          for (int n = sc.n; n > 0; n -= 2) {
+            const bool two = n > 1;
             ptx::mbar_wait(x_empty0 + 8u * s, ph ^ 1);
             if (lane == 0) {
-              ptx::mbar_arrive_expect_tx(x_full0 + 8u * s, xstage);
-              ptx::tma_load_2d(x_ring + s * xstage, xm, x_full0 + 8u * s, kb * 64, 0, ptx::kEvictLast);
+              const uint32_t full = x_full0 + 8u * s;
+              ptx::mbar_arrive_expect_tx(full, two ? 2 * xstage : xstage);
+              ptx::tma_load_2d(x_ring + (2 * s) * xstage, xm, full, kb * 64, 0, ptx::kEvictLast);
+              int kb2 = kb + 1;
+              if (kb2 == sc.kb) kb2 = 0;
+              if (two) ptx::tma_load_2d(x_ring + (2 * s + 1) * xstage, xm, full, kb2 * 64, 0, ptx::kEvictLast);
             }
             __syncwarp();
-            if (++s == static_cast<uint32_t>(nX)) { s = 0; ph ^= 1; }
-            if (++kb == sc.kb) kb = 0;
+            if (++s == (static_cast<uint32_t>(nX) >> 1)) { s = 0; ph ^= 1; }
+            kb += 2;
+            while (kb >= sc.kb) kb -= sc.kb;
           }
           if (lane == 0) MEGA_RSTAMP(l, kind * 8 + 1);
         }
@@ -792,49 +807,61 @@ __global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const __grid_c
     } else {
       const uint32_t idesc = ptx::umma_idesc_bf16(128, p.N);
       const uint64_t wdesc0 = ptx::umma_desc_k_sw128(w_ring), xdesc0 = ptx::umma_desc_k_sw128(x_ring);
-      uint32_t ws = 0, wph = 0, xs = 0, xph = 0, ait = 0;
+      uint32_t ws = 0, wph = 0, xs = 0, xph = 0, ait = 0;   // slot PAIRS and their phases
+      const uint32_t nWp = static_cast<uint32_t>(nW) >> 1, nXp = static_cast<uint32_t>(nX) >> 1;
 #pragma unroll 1
       for (int l = 0; l < p.L; ++l) {
 #pragma unroll 1
         for (int kind = 0; kind < 4; ++kind) {
           if (kind == 1) helper_attention(p, hc, cta, l, vgo, vdone);   // all c_attn MMAs of this CTA are issued
           const KindSched sc = sched[kind];
-          int n = sc.n, kb = sc.kb0;
+          int kb = sc.kb0;          // k block of the next unit inside its row tile
+          int seg_left = 0;         // units left in the current segment (0: the next unit opens one)
+          uint32_t buf = 0, tacc = 0;
 #pragma unroll 1
-          while (n > 0) {
-            int len = sc.kb - kb;
-            if (len > n) len = n;
-            const uint32_t buf = ait & 1, aph = (ait >> 1) & 1;
-            ++ait;
-            ptx::mbar_wait(t_empty0 + 8u * buf, aph ^ 1);
+          for (int n = sc.n; n > 0; n -= 2) {
+            const int cnt = n > 1 ? 2 : 1;
+            ptx::mbar_wait(w_full0 + 8u * ws, wph);
+            ptx::mbar_wait(x_full0 + 8u * xs, xph);
             ptx::tc_fence_after();
-            const uint32_t tacc = tmem_base + buf * static_cast<uint32_t>(p.N);
 #pragma unroll 1
-            for (int j = 0; j < len; ++j) {
-              ptx::mbar_wait(w_full0 + 8u * ws, wph);
-              ptx::mbar_wait(x_full0 + 8u * xs, xph);
-              ptx::tc_fence_after();
+            for (int u = 0; u < cnt; ++u) {
+              bool first = false;
+              if (seg_left == 0) {   // new segment: the rest of this row tile or of this CTA's range
+                seg_left = sc.kb - kb;
+                const int rest = n - u;
+                if (seg_left > rest) seg_left = rest;
+                buf = ait & 1;
+                const uint32_t aph = (ait >> 1) & 1;
+                ++ait;
+                ptx::mbar_wait(t_empty0 + 8u * buf, aph ^ 1);
+                ptx::tc_fence_after();
+                tacc = tmem_base + buf * static_cast<uint32_t>(p.N);
+                first = true;
+              }
+              --seg_left;
+              if (++kb == sc.kb) kb = 0;
               if (ptx::elect_one()) {
-                if (j == 0) MEGA_RSTAMP(l, kind * 8 + 2);
-                const uint64_t adesc = wdesc0 + static_cast<uint64_t>((ws * kWStage) >> 4);
-                const uint64_t bdesc = xdesc0 + static_cast<uint64_t>((xs * xstage) >> 4);
-                ptx::umma_bf16(tacc, adesc, bdesc, idesc, j > 0 ? 1u : 0u);
+                if (first) MEGA_RSTAMP(l, kind * 8 + 2);
+                const uint64_t adesc = wdesc0 + static_cast<uint64_t>(((2 * ws + u) * kWStage) >> 4);
+                const uint64_t bdesc = xdesc0 + static_cast<uint64_t>(((2 * xs + u) * xstage) >> 4);
+                ptx::umma_bf16(tacc, adesc, bdesc, idesc, first ? 0u : 1u);
                 ptx::umma_bf16(tacc, adesc + 2u, bdesc + 2u, idesc, 1u);
                 ptx::umma_bf16(tacc, adesc + 4u, bdesc + 4u, idesc, 1u);
                 ptx::umma_bf16(tacc, adesc + 6u, bdesc + 6u, idesc, 1u);
-                ptx::umma_commit(w_empty0 + 8u * ws);
-                ptx::umma_commit(x_empty0 + 8u * xs);
-                if (j == len - 1) {
+                if (seg_left == 0) {
                   ptx::umma_commit(t_full0 + 8u * buf);
                   MEGA_RSTAMP(l, kind * 8 + 3);
                 }
+                if (u == cnt - 1) {
+                  ptx::umma_commit(w_empty0 + 8u * ws);
+                  ptx::umma_commit(x_empty0 + 8u * xs);
+                }
               }
               __syncwarp();
-              if (++ws == static_cast<uint32_t>(nW)) { ws = 0; wph ^= 1; }
-              if (++xs == static_cast<uint32_t>(nX)) { xs = 0; xph ^= 1; }
             }
-            n -= len;
-            kb = 0;
+            if (++ws == nWp) { ws = 0; wph ^= 1; }
+            if (++xs == nXp) { xs = 0; xph ^= 1; }
           }
         }
       }
@@ -967,10 +994,11 @@ int mega_launch(const MegaParams& p_in, cudaStream_t s) {
   const int total = 227 * 1024 - 1024 /*alignment*/;
   const int xstage = p.N * 128;
   const int fixed = kAttnWarps * 192 * 4 + 64 + 64 + kTblMax * 4 + 512;
-  p.nX = p.N <= 64 ? 8 : p.N <= 128 ? 4 : 3;
+  p.nX = p.N <= 64 ? 8 : p.N <= 128 ? 4 : 2;   // even: slots are handed over in pairs
   p.xring_bytes = p.nX * xstage > kVecScratch ? p.nX * xstage : kVecScratch;
   p.nW = (total - fixed - p.xring_bytes) / kWStage;
   if (p.nW > 12) p.nW = 12;
+  p.nW &= ~1;                       // slots are handed over in pairs
   if (p.nW < 2) return static_cast<int>(cudaErrorInvalidValue);
   {
     const char* dbg = getenv("CCB_MEGA_DEBUG");

@@ -840,7 +840,7 @@ int ccb_create(ccb_ctx** out, const ccb_model_desc* desc, int device) {
   MegaState& mg = c->mega;
   if (D.lm_arch == CCB_LM_GPT2 && lm_hd == 64 && d <= 4096 && mega_init() == 0) {
     mega_plan(mg, d, 4 * d, c->num_sms);
-    if (mg.tbl_entries <= 512) {
+    if (mg.tbl_entries <= 256) {
       mg.max_rows = std::min(c->max_rows, 256);
       mg.d_wmaps = static_cast<CUtensorMap*>(a.take(sizeof(CUtensorMap) * 4 * D.lm_layers));
       mg.d_layers = a.arr<MegaLayer>(D.lm_layers);
