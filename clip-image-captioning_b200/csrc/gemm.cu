@@ -1,10 +1,12 @@
 // Host side of the tcgen05 GEMM: tensor-map encoding, orientation / tile / split-K selection, launch.
 #include <cuda.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
 
+#include "gemm_persist.cuh"
 #include "gemm_sm100.cuh"
 #include "internal.h"
 #include "mega.h"
@@ -86,6 +88,83 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, di
   return 0;
 }
 
+
+// Tile width BN (and kernel variant) for the persistent kernels, from the B200 sweeps of tools/sweep_gemm_bn.py.  A round
+// of tiles costs k_blocks x the time of one k-block, which is bound by the SM's shared-memory port (TMA writes and MMA
+// reads of 16 KB + BN x 128 B each), i.e. proportional to 16 + BN / 8, plus a small hand-over; the number of rounds is
+// ceil(tiles / SMs).  The widest candidate wins ties.  The CTA-pair kernel (256-token tiles, half the W bytes per SM)
+// measured within +-3 % of the single-CTA kernel everywhere and ahead of it only for long K, where it is used.
+void pick_persist(int tokens, int features, int k_blocks, int num_sms, int force_orientation, int force_bn, bool* pair_out,
+                  int* bn_out) {
+  const int m_tiles = (tokens + 127) / 128;
+  long long best = 0;
+  int best_bn = 0;
+  for (int bn = 256; bn >= 64; bn -= 32) {
+    if (force_bn && bn != force_bn) continue;
+    const long long tiles = static_cast<long long>(m_tiles) * ((features + bn - 1) / bn);
+    const long long rounds = (tiles + num_sms - 1) / num_sms;
+    const long long cost = rounds * (16 + bn / 8 + 2);
+    if (best_bn == 0 || cost < best) {
+      best = cost;
+      best_bn = bn;
+    }
+  }
+  *bn_out = best_bn;
+  *pair_out = force_orientation == 3 || (force_orientation != 4 && best_bn == 256 && k_blocks >= 64 && tokens >= 512 &&
+                                         ((tokens + 255) / 256) * ((features + 255) / 256) <= num_sms / 2);
+}
+
+int launch_persist(const GemmArgs& a, const GemmParams& p_in, int bn, bool pair, int num_sms, cudaStream_t s) {
+  PersistParams pp;
+  memset(&pp, 0, sizeof(pp));
+  pp.g = p_in;
+  pp.g.split_k = 1;
+  pp.bn = bn;
+  const int stage_bytes = 128 * 128 + bn * (pair ? 64 : 128);
+  int stages = (kPersistSmemBytes - 1024 - 512) / stage_bytes;
+  if (stages > 8) stages = 8;
+  pp.stages = stages;
+  pp.m_tiles = pair ? (a.tokens + 255) / 256 : (a.tokens + 127) / 128;
+  pp.n_tiles = (a.features + bn - 1) / bn;
+  {
+    const char* dbg = getenv("CCB_GEMM_DEBUG");
+    pp.debug = dbg ? atoi(dbg) : 0;
+  }
+  CUtensorMap tx, tw;
+  if (make_tmap(&tx, a.act, a.tokens, a.K, a.lda, 128)) return -1;
+  if (make_tmap(&tw, a.weight, a.features, a.K, a.K, pair ? bn / 2 : bn)) return -1;
+  const int tiles = pp.m_tiles * pp.n_tiles;
+  const int units = pair ? num_sms / 2 : num_sms;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((tiles < units ? tiles : units) * (pair ? 2 : 1));
+  cfg.blockDim = dim3(kPersistThreads);
+  cfg.dynamicSmemBytes = static_cast<size_t>(stages) * stage_bytes + 1024 + 512;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (pair) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pp.g.pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  cudaError_t e = pair ? cudaLaunchKernelEx(&cfg, gemm_pair_kernel, tx, tw, pp) : cudaLaunchKernelEx(&cfg, gemm_persist_kernel, tx, tw, pp);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail("persistent GEMM launch failed: %s", cudaGetErrorString(e));
+  }
+  return 0;
+}
+
 }  // namespace
 
 const char* gemm_last_error() { return g_err; }
@@ -111,6 +190,9 @@ int gemm_init(int device) {
     r |= set_attr<64>();
     r |= set_attr<128>();
     r |= set_attr<256>();
+    if (cudaFuncSetAttribute(gemm_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPersistSmemBytes) != cudaSuccess ||
+        cudaFuncSetAttribute(gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPersistSmemBytes) != cudaSuccess)
+      r |= fail("cudaFuncSetAttribute(smem) failed for the persistent GEMM");
     g_attr_status = r;
   });
   return g_attr_status;
@@ -121,6 +203,7 @@ int gemm_launch(const GemmArgs& a, const GemmWorkspace& w, cudaStream_t stream) 
   if (a.K <= 0 || a.K % 64 != 0) return fail("GEMM K must be a positive multiple of 64");
   if (a.tokens <= 0 || a.features <= 0) return fail("GEMM with empty extent");
 
+  // force_orientation: 0 auto, 1 normal, 2 swapped, 3 normal + CTA-pair persistent kernel, 4 normal + single-CTA persistent
   const bool swapped = a.force_orientation ? (a.force_orientation == 2) : (a.tokens <= 256);
   if (swapped && a.rg_in > 0) return fail("row remap is only supported in the normal orientation");
   if (swapped && a.tokens > 256) return fail("swapped orientation needs tokens <= 256");
@@ -133,7 +216,10 @@ int gemm_launch(const GemmArgs& a, const GemmWorkspace& w, cudaStream_t stream) 
   } else {
     bn = a.features >= 256 ? 256 : a.features > 64 ? 128 : 64;
   }
-  if (bn != 32 && bn != 64 && bn != 128 && bn != 256) return fail("unsupported BN");
+  // token-heavy contractions (ViT / mapper / prefill) take the persistent kernel; force_split pins the
+  // one-tile-per-CTA kernel (tuning / A-B)
+  const bool persist = !swapped && a.force_split == 0;
+  if (!persist && bn != 32 && bn != 64 && bn != 128 && bn != 256) return fail("unsupported BN");
   if (swapped && bn < a.tokens) return fail("swapped orientation: BN smaller than token count");
 
   GemmParams p;
@@ -163,6 +249,14 @@ int gemm_launch(const GemmArgs& a, const GemmWorkspace& w, cudaStream_t stream) 
     if ((reinterpret_cast<uintptr_t>(a.out) & 15) || (a.residual && (reinterpret_cast<uintptr_t>(a.residual) & 15)) ||
         (a.bias && (reinterpret_cast<uintptr_t>(a.bias) & 15)))
       return fail("normal-orientation GEMM needs 16-byte aligned out / residual / bias");
+  }
+
+  if (persist) {
+    bool pair = a.force_orientation == 3;
+    int pbn = a.force_bn;
+    if (a.force_orientation < 3 || pbn == 0) pick_persist(a.tokens, a.features, p.k_blocks, w.num_sms, a.force_orientation, a.force_bn, &pair, &pbn);
+    if (pbn < 32 || pbn > 256 || pbn % 32) return fail("unsupported BN for the persistent GEMM");
+    return launch_persist(a, p, pbn, pair, w.num_sms, stream);
   }
 
   dim3 grid((p.Ra + 127) / 128, (p.Rb + bn - 1) / bn, 1);

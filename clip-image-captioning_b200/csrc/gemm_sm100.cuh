@@ -133,22 +133,46 @@ __device__ __forceinline__ void gemm_epilogue_cols(const GemmParams& p, float (&
         acc[v] += r4.x; acc[v + 1] += r4.y; acc[v + 2] += r4.z; acc[v + 3] += r4.w;
       }
     }
+    // Whole 32-byte sectors per store instruction where the row allows it (256-bit st.global): a 16-byte store
+    // is a PARTIAL sector write, which L2 has to merge (and, for a sector that is not resident, fill from DRAM first);
+    // with thread = row every lane of a store hits a different sector, so the 16-byte form doubled the write requests
+    // and cost the persistent kernels 20 % although the epilogue runs underneath the main loop.
     if (p.out_bf16) {
       __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + out_row * p.ldo + j0;
+      if (CW % 16 == 0 && (reinterpret_cast<uintptr_t>(o) & 31) == 0) {
 #pragma unroll
-      for (int v = 0; v < CW; v += 8) {
-        uint4 pk;
-        pk.x = pack_bf16x2(acc[v], acc[v + 1]);
-        pk.y = pack_bf16x2(acc[v + 2], acc[v + 3]);
-        pk.z = pack_bf16x2(acc[v + 4], acc[v + 5]);
-        pk.w = pack_bf16x2(acc[v + 6], acc[v + 7]);
-        *reinterpret_cast<uint4*>(o + v) = pk;
+        for (int v = 0; v + 16 <= CW; v += 16) {
+          uint32_t k[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) k[e] = pack_bf16x2(acc[v + 2 * e], acc[v + 2 * e + 1]);
+          ptx::st_global_256(o + v, k);
+        }
+      } else {
+#pragma unroll
+        for (int v = 0; v < CW; v += 8) {
+          uint4 pk;
+          pk.x = pack_bf16x2(acc[v], acc[v + 1]);
+          pk.y = pack_bf16x2(acc[v + 2], acc[v + 3]);
+          pk.z = pack_bf16x2(acc[v + 4], acc[v + 5]);
+          pk.w = pack_bf16x2(acc[v + 6], acc[v + 7]);
+          *reinterpret_cast<uint4*>(o + v) = pk;
+        }
       }
     } else {
       float* o = reinterpret_cast<float*>(p.out) + out_row * p.ldo + j0;
+      if (CW % 8 == 0 && (reinterpret_cast<uintptr_t>(o) & 31) == 0) {
 #pragma unroll
-      for (int v = 0; v < CW; v += 4)
-        *reinterpret_cast<float4*>(o + v) = make_float4(acc[v], acc[v + 1], acc[v + 2], acc[v + 3]);
+        for (int v = 0; v + 8 <= CW; v += 8) {
+          uint32_t k[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) k[e] = __float_as_uint(acc[v + e]);
+          ptx::st_global_256(o + v, k);
+        }
+      } else {
+#pragma unroll
+        for (int v = 0; v < CW; v += 4)
+          *reinterpret_cast<float4*>(o + v) = make_float4(acc[v], acc[v + 1], acc[v + 2], acc[v + 3]);
+      }
     }
   } else {
     if (p.residual) {

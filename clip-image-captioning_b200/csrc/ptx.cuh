@@ -146,11 +146,67 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
          | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+
+// ---------------------------------------------------------------- CTA pairs (cta_group::2)
+// Two CTAs of one cluster (ranks 0 / 1, one TPC) issue ONE tcgen05.mma of M = 256: each CTA holds its 128 rows of A,
+// its half of the B rows and its 128 accumulator lanes; the instruction is issued by the leader (rank 0) only, with
+// shared-memory descriptors relative to the leader's window (the peer uses the same offsets).
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+template <int kCols>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_slot) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_slot), "n"(kCols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int kCols>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the mbarrier at this shared-memory offset in every CTA of `cta_mask` once the issued MMAs completed
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(cta_mask)
+               : "memory");
+}
+// TMA load into THIS CTA's shared memory that completes its bytes on an mbarrier of the pair's leader
+// (`bar_cluster` is a shared::cluster address, e.g. from mapa_shared(bar, 0))
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar_cluster, int c0, int c1,
+                                                 uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster), "r"(c0), "r"(c1), "l"(hint)
+      : "memory");
+}
+// arrive (count 1) on an mbarrier given by its shared::cluster address (possibly in the peer CTA)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
+
 // ---------------------------------------------------------------- misc global memory
 __device__ __forceinline__ float ldcg_f32(const float* p) {
   float v;
   asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));
   return v;
+}
+// 256-bit store (sm_100+): one whole 32-byte sector per lane
+__device__ __forceinline__ void st_global_256(void* p, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+               "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
 }
 __device__ __forceinline__ uint4 ld_nc_u4(const void* p) {
   uint4 v;

@@ -40,6 +40,22 @@ LINEAR_CASES = [
     (256, 50257, 128, 2, 256, 1),    # lm_head shape, swapped with odd vocab
     (200, 1000, 512, 1, 128, 2),     # split-K normal
     (49, 768, 3072, 0, 0, 0),        # ViT patch embed at batch 1
+    # persistent kernel (normal orientation, split_k = 0): auto and forced tile widths, ragged edges, many tiles per CTA
+    (300, 520, 256, 1, 0, 0),
+    (300, 520, 256, 1, 64, 0),
+    (1000, 100, 128, 1, 96, 0),
+    (130, 96, 64, 1, 0, 0),
+    (2560, 4800, 1600, 1, 0, 0),     # GPT2-XL prefill c_attn
+    (3200, 768, 768, 1, 0, 0),       # ViT attention projection at batch 64
+    (5120, 6400, 1600, 1, 224, 0),   # mapper MLP, 5 stages
+    (20000, 512, 192, 4, 32, 0),     # 2512 tiles: 17 per CTA, both accumulator buffers, ring wrap-around
+    # CTA-pair kernel (cta_group::2, 256-token tiles)
+    (300, 520, 256, 3, 64, 0),
+    (2560, 4800, 1600, 3, 256, 0),
+    (3200, 768, 768, 3, 96, 0),      # 12.5 pair tiles: the last peer CTA is entirely out of range
+    (1000, 100, 128, 3, 128, 0),
+    (20000, 512, 192, 3, 32, 0),
+    (5120, 6400, 1600, 3, 224, 0),
 ]
 
 

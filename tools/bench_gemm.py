@@ -33,5 +33,5 @@ for features, K in cases:
         e1.record()
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) * 1e3 / (reps * n)
-        print("tokens %d features %d K %d split %s: %.2f us  %.0f GB/s (weights only)" % (tokens, features, K, s or "auto", us, features * K * 2 / us / 1e3))
+        print("tokens %d features %d K %d split %s: %.2f us  %.0f GB/s (weights only)  %.0f TFLOP/s" % (tokens, features, K, s or "auto", us, features * K * 2 / us / 1e3, 2.0 * tokens * features * K / us / 1e6))
     del W
