@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) gemm_persist_kernel(const 
     // ------------------------------------------------------------ TMA producers: warp 0 loads X, warp 6 loads W
     // (one thread issues a tensor load every ~130 ns; two loads per k-block from one thread would pace the ring at
     //  the speed of the MMAs themselves, so each operand has its own issuing thread)
-    if (lane == 0) {
+    {
       const bool is_x = warp == 0;
       // weights never depend on the preceding kernel: with PDL their tiles are requested ahead of the dependency wait
       if (is_x) ptx::grid_dep_wait();
@@ -124,16 +124,21 @@ __global__ void __launch_bounds__(kPersistThreads, 1) gemm_persist_kernel(const 
       const uint32_t off = is_x ? 0u : 128u * 128u;
       const uint64_t hint = is_x ? ptx::kEvictLast : ptx::kEvictNormal;
       uint32_t s = 0, ph = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+#pragma unroll 1
+      for (int tile = blockIdx.x; tile < ntiles && (pp.debug & 64) == 0; tile += gridDim.x) {
         const int row = is_x ? (tile % pp.m_tiles) * 128 : (tile / pp.m_tiles) * BN;
+#pragma unroll 1
         for (int kb = 0; kb < nkb; ++kb) {
           ptx::mbar_wait(empty0 + 8u * s, ph ^ 1);
-          if (pp.debug & 1) {   // tuning: no TMA loads
-            if (is_x) ptx::mbar_arrive(full0 + 8u * s);
-          } else {
-            if (is_x) ptx::mbar_arrive_expect_tx(full0 + 8u * s, stage_bytes);
-            ptx::tma_load_2d(smem_base + s * stage_bytes + off, tm, full0 + 8u * s, kb * 64, row, hint);
+          if (ptx::elect_one()) {
+            if (pp.debug & 1) {   // tuning: no TMA loads
+              if (is_x) ptx::mbar_arrive(full0 + 8u * s);
+            } else {
+              if (is_x) ptx::mbar_arrive_expect_tx(full0 + 8u * s, stage_bytes);
+              ptx::tma_load_2d(smem_base + s * stage_bytes + off, tm, full0 + 8u * s, kb * 64, row, hint);
+            }
           }
+          __syncwarp();
           if (++s == static_cast<uint32_t>(S)) { s = 0; ph ^= 1; }
         }
       }
@@ -141,32 +146,41 @@ __global__ void __launch_bounds__(kPersistThreads, 1) gemm_persist_kernel(const 
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // The whole (converged) warp runs the loops and waits; one elected lane issues.  Everything the issue needs is
+    // warp-uniform, so the compiler keeps it in uniform registers and emits the tcgen05 instructions back to back; under
+    // `if (lane == 0)` every descriptor went through R2UR and every instruction through its own election loop, which
+    // cost ~0.3 us per k-block -- as much as the MMAs of a 256-wide tile and 3x those of a 64-wide one.
+    {
       const uint32_t idesc = ptx::umma_idesc_bf16(128, BN);
+      const uint64_t desc0 = ptx::umma_desc_k_sw128(smem_base);
       uint32_t s = 0, ph = 0, it = 0;
+#pragma unroll 1
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const uint32_t buf = it & 1, aph = (it >> 1) & 1;
         ptx::mbar_wait(tempty0 + 8u * buf, aph ^ 1);   // the epilogue drained this accumulator
         ptx::tc_fence_after();
         const uint32_t tacc = tmem_base + buf * 256u;
+#pragma unroll 1
         for (int kb = 0; kb < nkb; ++kb) {
-          ptx::mbar_wait(full0 + 8u * s, ph);
+          if ((pp.debug & 64) == 0) ptx::mbar_wait(full0 + 8u * s, ph);   // (64: tuning, free-running issue loop)
           ptx::tc_fence_after();
-          const uint32_t sa = smem_base + s * stage_bytes;
-          const uint64_t adesc = ptx::umma_desc_k_sw128(sa);
-          const uint64_t bdesc = ptx::umma_desc_k_sw128(sa + 128u * 128u);
-          if ((pp.debug & 2) == 0) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              ptx::umma_bf16(tacc, adesc + 2u * k, bdesc + 2u * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          if (ptx::elect_one()) {
+            const uint64_t adesc = desc0 + static_cast<uint64_t>((s * stage_bytes) >> 4);
+            const uint64_t bdesc = adesc + static_cast<uint64_t>((128u * 128u) >> 4);
+            if ((pp.debug & 2) == 0) {
+              ptx::umma_bf16(tacc, adesc, bdesc, idesc, kb > 0 ? 1u : 0u);
+              ptx::umma_bf16(tacc, adesc + 2u, bdesc + 2u, idesc, 1u);
+              ptx::umma_bf16(tacc, adesc + 4u, bdesc + 4u, idesc, 1u);
+              ptx::umma_bf16(tacc, adesc + 6u, bdesc + 6u, idesc, 1u);
+            }
+            if ((pp.debug & 64) == 0) ptx::umma_commit(empty0 + 8u * s);
+            if (kb == nkb - 1) ptx::umma_commit(tfull0 + 8u * buf);
           }
-          ptx::umma_commit(empty0 + 8u * s);
+          __syncwarp();
           if (++s == static_cast<uint32_t>(S)) { s = 0; ph ^= 1; }
         }
-        ptx::umma_commit(tfull0 + 8u * buf);
       }
     }
-    __syncwarp();
   } else {
     // ------------------------------------------------------------ epilogue warps
     ptx::grid_dep_wait();   // residual / out belong to the preceding kernels of the chain

@@ -57,6 +57,21 @@ __global__ void __launch_bounds__(256, 1) bar_kernel(unsigned* ctr, unsigned* fl
       __syncthreads();
       if ((t & 31) == 0) { unsigned* c = ctr + (t >> 5) * 32; red_release(c, 1); while (ld_acquire(c) < (unsigned)it * n) {} }
       __syncwarp();
+    } else if (V == 7 || V == 8 || V == 9) {  // sharded counters 128 B apart (V7: 16, V8: 8, V9: 32): CTA c arrives on shard c % S,
+                                              // one warp polls all shards (lane k waits for shard k's share)
+      constexpr int S = V == 7 ? 16 : V == 8 ? 8 : 32;
+      __syncthreads();
+      if (t == 0) red_release(ctr + 2048 + (cta % S) * 32, 1);
+      if (t < 32) {
+        const unsigned share = t < S ? (unsigned)((n - t + S - 1) / S) : 0u;
+        const unsigned* c = ctr + 2048 + (t % S) * 32;
+        bool done;
+        do {
+          done = t >= S || ld_acquire(c) >= (unsigned)it * share;
+          done = __all_sync(0xffffffffu, done);
+        } while (!done);
+      }
+      __syncthreads();
     }
     // check: read what CTA (cta+1)%n wrote this iteration (through L2)
     float v;
@@ -92,7 +107,7 @@ int main() {
   cudaMemset(err, 0, 4);
   const int iters = 2000;
   // baseline: the fixed second barrier (variant 0 style) costs the same in every variant; report total per iteration
-  float t[7];
+  float t[10];
   run<0>(ctr, flags, data, err, 100);
   t[0] = run<0>(ctr, flags, data, err, iters);
   t[1] = run<1>(ctr, flags, data, err, iters);
@@ -101,12 +116,15 @@ int main() {
   t[4] = run<4>(ctr, flags, data, err, iters);
   t[5] = run<5>(ctr, flags, data, err, iters);
   t[6] = run<6>(ctr, flags, data, err, iters);
+  t[7] = run<7>(ctr, flags, data, err, iters);
+  t[8] = run<8>(ctr, flags, data, err, iters);
+  t[9] = run<9>(ctr, flags, data, err, iters);
   unsigned herr; cudaMemcpy(&herr, err, 4, cudaMemcpyDeviceToHost);
-  const char* names[7] = {"t0 red.release + ld.acquire poll", "relaxed poll + fence", "fence + red.relaxed, relaxed poll + fence",
-                          "8 pollers (lane 0 per warp)", "per-CTA flags, one warp reads all", "threadfence + atomicAdd + volatile poll", "8 counters, per-warp"};
+  const char* names[10] = {"t0 red.release + ld.acquire poll", "relaxed poll + fence", "fence + red.relaxed, relaxed poll + fence",
+                          "8 pollers (lane 0 per warp)", "per-CTA flags, one warp reads all", "threadfence + atomicAdd + volatile poll", "8 counters, per-warp", "16 sharded counters, one warp polls", "8 sharded counters", "32 sharded counters"};
   // every iteration = variant barrier + one V0-style barrier: V0 total / 2 = cost of one V0 barrier
   const float v0 = t[0] / iters / 2 * 1000;
-  for (int i = 0; i < 7; ++i) printf("variant %d (%s): %.3f us per barrier\n", i, names[i], t[i] / iters * 1000 - v0);
+  for (int i = 0; i < 10; ++i) printf("variant %d (%s): %.3f us per barrier\n", i, names[i], t[i] / iters * 1000 - v0);
   printf("ordering errors: %u (%s)\n", herr, cudaGetErrorString(cudaGetLastError()));
   return 0;
 }
