@@ -805,10 +805,16 @@ __global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const __grid_c
     if (skip_gemm) {
       for (int l = 0; l < p.L; ++l) helper_attention(p, hc, cta, l, vgo, vdone);
     } else {
+      // The issue loop is instruction bound (one warp, dependent address arithmetic in front of every tcgen05.mma), so
+      // it works on slot PAIRS: one set of waits, one descriptor computation (kept incrementally, no multiplies) and
+      // one pair of ring commits per two units; the segment bookkeeping of both units is done ahead of the waits.
       const uint32_t idesc = ptx::umma_idesc_bf16(128, p.N);
       const uint64_t wdesc0 = ptx::umma_desc_k_sw128(w_ring), xdesc0 = ptx::umma_desc_k_sw128(x_ring);
+      const uint64_t wstep = static_cast<uint64_t>(kWStage >> 4), xstep = static_cast<uint64_t>(xstage >> 4);
+      uint64_t wd = wdesc0, xd = xdesc0;                    // descriptors of the current slot pair
       uint32_t ws = 0, wph = 0, xs = 0, xph = 0, ait = 0;   // slot PAIRS and their phases
       const uint32_t nWp = static_cast<uint32_t>(nW) >> 1, nXp = static_cast<uint32_t>(nX) >> 1;
+      const uint32_t nacc = static_cast<uint32_t>(p.N);
 #pragma unroll 1
       for (int l = 0; l < p.L; ++l) {
 #pragma unroll 1
@@ -817,51 +823,66 @@ __global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const __grid_c
           const KindSched sc = sched[kind];
           int kb = sc.kb0;          // k block of the next unit inside its row tile
           int seg_left = 0;         // units left in the current segment (0: the next unit opens one)
-          uint32_t buf = 0, tacc = 0;
+          uint32_t buf = 0;
 #pragma unroll 1
           for (int n = sc.n; n > 0; n -= 2) {
-            const int cnt = n > 1 ? 2 : 1;
+            const bool two = n > 1;
+            // ---- segment bookkeeping of both units (a segment = the rest of a row tile or of this CTA's range)
+            bool first0 = false, first1 = false;
+            if (seg_left == 0) {
+              seg_left = sc.kb - kb;
+              if (seg_left > n) seg_left = n;
+              buf = ait & 1;
+              ptx::mbar_wait(t_empty0 + 8u * buf, ((ait >> 1) & 1) ^ 1);
+              ++ait;
+              first0 = true;
+            }
+            const uint32_t buf0 = buf;
+            const bool end0 = --seg_left == 0;
+            if (++kb == sc.kb) kb = 0;
+            bool end1 = false;
+            if (two) {
+              if (seg_left == 0) {
+                seg_left = sc.kb - kb;
+                if (seg_left > n - 1) seg_left = n - 1;
+                buf = ait & 1;
+                ptx::mbar_wait(t_empty0 + 8u * buf, ((ait >> 1) & 1) ^ 1);
+                ++ait;
+                first1 = true;
+              }
+              end1 = --seg_left == 0;
+              if (++kb == sc.kb) kb = 0;
+            }
+            const uint32_t buf1 = buf;
             ptx::mbar_wait(w_full0 + 8u * ws, wph);
             ptx::mbar_wait(x_full0 + 8u * xs, xph);
             ptx::tc_fence_after();
-#pragma unroll 1
-            for (int u = 0; u < cnt; ++u) {
-              bool first = false;
-              if (seg_left == 0) {   // new segment: the rest of this row tile or of this CTA's range
-                seg_left = sc.kb - kb;
-                const int rest = n - u;
-                if (seg_left > rest) seg_left = rest;
-                buf = ait & 1;
-                const uint32_t aph = (ait >> 1) & 1;
-                ++ait;
-                ptx::mbar_wait(t_empty0 + 8u * buf, aph ^ 1);
-                ptx::tc_fence_after();
-                tacc = tmem_base + buf * static_cast<uint32_t>(p.N);
-                first = true;
+            if (ptx::elect_one()) {
+              if (first0) MEGA_RSTAMP(l, kind * 8 + 2);
+              const uint32_t tacc0 = tmem_base + buf0 * nacc;
+              ptx::umma_bf16(tacc0, wd, xd, idesc, first0 ? 0u : 1u);
+              ptx::umma_bf16(tacc0, wd + 2u, xd + 2u, idesc, 1u);
+              ptx::umma_bf16(tacc0, wd + 4u, xd + 4u, idesc, 1u);
+              ptx::umma_bf16(tacc0, wd + 6u, xd + 6u, idesc, 1u);
+              if (end0) ptx::umma_commit(t_full0 + 8u * buf0);
+              if (two) {
+                const uint32_t tacc1 = tmem_base + buf1 * nacc;
+                const uint64_t wd1 = wd + wstep, xd1 = xd + xstep;
+                ptx::umma_bf16(tacc1, wd1, xd1, idesc, first1 ? 0u : 1u);
+                ptx::umma_bf16(tacc1, wd1 + 2u, xd1 + 2u, idesc, 1u);
+                ptx::umma_bf16(tacc1, wd1 + 4u, xd1 + 4u, idesc, 1u);
+                ptx::umma_bf16(tacc1, wd1 + 6u, xd1 + 6u, idesc, 1u);
+                if (end1) ptx::umma_commit(t_full0 + 8u * buf1);
               }
-              --seg_left;
-              if (++kb == sc.kb) kb = 0;
-              if (ptx::elect_one()) {
-                if (first) MEGA_RSTAMP(l, kind * 8 + 2);
-                const uint64_t adesc = wdesc0 + static_cast<uint64_t>(((2 * ws + u) * kWStage) >> 4);
-                const uint64_t bdesc = xdesc0 + static_cast<uint64_t>(((2 * xs + u) * xstage) >> 4);
-                ptx::umma_bf16(tacc, adesc, bdesc, idesc, first ? 0u : 1u);
-                ptx::umma_bf16(tacc, adesc + 2u, bdesc + 2u, idesc, 1u);
-                ptx::umma_bf16(tacc, adesc + 4u, bdesc + 4u, idesc, 1u);
-                ptx::umma_bf16(tacc, adesc + 6u, bdesc + 6u, idesc, 1u);
-                if (seg_left == 0) {
-                  ptx::umma_commit(t_full0 + 8u * buf);
-                  MEGA_RSTAMP(l, kind * 8 + 3);
-                }
-                if (u == cnt - 1) {
-                  ptx::umma_commit(w_empty0 + 8u * ws);
-                  ptx::umma_commit(x_empty0 + 8u * xs);
-                }
-              }
-              __syncwarp();
+              ptx::umma_commit(w_empty0 + 8u * ws);
+              ptx::umma_commit(x_empty0 + 8u * xs);
+              if (n <= 2) MEGA_RSTAMP(l, kind * 8 + 3);
             }
-            if (++ws == nWp) { ws = 0; wph ^= 1; }
-            if (++xs == nXp) { xs = 0; xph ^= 1; }
+            __syncwarp();
+            wd += 2 * wstep;
+            xd += 2 * xstep;
+            if (++ws == nWp) { ws = 0; wph ^= 1; wd = wdesc0; }
+            if (++xs == nXp) { xs = 0; xph ^= 1; xd = xdesc0; }
           }
         }
       }

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <vector>
 #include "ptx.cuh"
 using namespace ccb;
@@ -115,6 +116,11 @@ int main() {
   // A[r, k] = (r + 1) if k == 0 else 0;  B[n, k] = (n + 1) if k == 0 else 0  ->  D[r, n] = (r + 1) * (n + 1) (exact in bf16 for small values)
   for (int r = 0; r < 128; ++r) for (int k = 0; k < 64; ++k) ha[r * 64 + k] = __float2bfloat16(k == 0 ? float(r + 1) : 0.f);
   for (int n = 0; n < 256; ++n) for (int k = 0; k < 64; ++k) hb[n * 64 + k] = __float2bfloat16(k == 0 ? (n < 8 ? float(n + 1) : 1.f) : 0.f);
+  if (getenv("RANDOM_OPERANDS")) {
+    srand(1);
+    for (auto& v : ha) v = __float2bfloat16((rand() % 2001 - 1000) * 1e-3f);
+    for (auto& v : hb) v = __float2bfloat16((rand() % 2001 - 1000) * 1e-3f);
+  }
   __nv_bfloat16 *da, *db; long long* dc; float* dd;
   cudaMalloc(&da, ha.size() * 2); cudaMalloc(&db, hb.size() * 2); cudaMalloc(&dc, 16); cudaMalloc(&dd, 128 * 256 * 4);
   cudaMemcpy(da, ha.data(), ha.size() * 2, cudaMemcpyHostToDevice);
