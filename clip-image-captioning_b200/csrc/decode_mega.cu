@@ -649,6 +649,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const __grid_c
   const uint32_t base = (raw_u32 + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - raw_u32);
   const int nW = p.nW, nX = p.nX;
+  const int grp = p.grp;   // units per ring hand-over: 2 (slot pairs) or 1 (256 rows: the X ring holds only three tiles)
   const uint32_t xstage = static_cast<uint32_t>(p.N) * 128u;
   const uint32_t w_ring = base;
   const uint32_t x_ring = w_ring + nW * kWStage;
@@ -723,7 +724,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const __grid_c
     // half the waits, expect_tx and commits per byte in all three role loops, which are what paces a GEMM phase.
     if (!skip_gemm) {
       uint32_t sp = 0, ph = 0;   // slot pair, its phase
-      const uint32_t nWp = static_cast<uint32_t>(nW) >> 1;
+      const uint32_t nWp = static_cast<uint32_t>(nW / grp);
 #pragma unroll 1
       for (int l = 0; l < p.L; ++l) {
 #pragma unroll 1
@@ -732,20 +733,20 @@ __global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const __grid_c
           const KindSched sc = sched[kind];
           int tile = sc.tile0, kb = sc.kb0;
 #pragma unroll 1
-          for (int n = sc.n; n > 0; n -= 2) {
-            const bool two = n > 1;
+          for (int n = sc.n; n > 0; n -= grp) {
+            const bool two = grp == 2 && n > 1;
             ptx::mbar_wait(w_empty0 + 8u * sp, ph ^ 1);
             if (ptx::elect_one()) {
               const uint32_t full = w_full0 + 8u * sp;
               ptx::mbar_arrive_expect_tx(full, two ? 2 * kWStage : kWStage);
-              ptx::tma_load_2d(w_ring + (2 * sp) * kWStage, wm, full, kb * 64, tile * 128, ptx::kEvictFirst);
+              ptx::tma_load_2d(w_ring + (grp * sp) * kWStage, wm, full, kb * 64, tile * 128, ptx::kEvictFirst);
               int kb2 = kb + 1, tile2 = tile;
               if (kb2 == sc.kb) { kb2 = 0; ++tile2; }
-              if (two) ptx::tma_load_2d(w_ring + (2 * sp + 1) * kWStage, wm, full, kb2 * 64, tile2 * 128, ptx::kEvictFirst);
+              if (two) ptx::tma_load_2d(w_ring + (grp * sp + 1) * kWStage, wm, full, kb2 * 64, tile2 * 128, ptx::kEvictFirst);
             }
             __syncwarp();
             if (++sp == nWp) { sp = 0; ph ^= 1; }
-            kb += 2;
+            kb += grp;
             while (kb >= sc.kb) { kb -= sc.kb; ++tile; }
           }
         }
@@ -778,20 +779,20 @@ __global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const __grid_c
           __syncwarp();
           int kb = sc.kb0;
 #pragma unroll 1
-          for (int n = sc.n; n > 0; n -= 2) {
-            const bool two = n > 1;
+          for (int n = sc.n; n > 0; n -= grp) {
+            const bool two = grp == 2 && n > 1;
             ptx::mbar_wait(x_empty0 + 8u * s, ph ^ 1);
             if (lane == 0) {
               const uint32_t full = x_full0 + 8u * s;
               ptx::mbar_arrive_expect_tx(full, two ? 2 * xstage : xstage);
-              ptx::tma_load_2d(x_ring + (2 * s) * xstage, xm, full, kb * 64, 0, ptx::kEvictLast);
+              ptx::tma_load_2d(x_ring + (grp * s) * xstage, xm, full, kb * 64, 0, ptx::kEvictLast);
               int kb2 = kb + 1;
               if (kb2 == sc.kb) kb2 = 0;
-              if (two) ptx::tma_load_2d(x_ring + (2 * s + 1) * xstage, xm, full, kb2 * 64, 0, ptx::kEvictLast);
+              if (two) ptx::tma_load_2d(x_ring + (grp * s + 1) * xstage, xm, full, kb2 * 64, 0, ptx::kEvictLast);
             }
             __syncwarp();
-            if (++s == (static_cast<uint32_t>(nX) >> 1)) { s = 0; ph ^= 1; }
-            kb += 2;
+            if (++s == static_cast<uint32_t>(nX / grp)) { s = 0; ph ^= 1; }
+            kb += grp;
             while (kb >= sc.kb) kb -= sc.kb;
           }
           if (lane == 0) MEGA_RSTAMP(l, kind * 8 + 1);
@@ -813,7 +814,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const __grid_c
       const uint64_t wstep = static_cast<uint64_t>(kWStage >> 4), xstep = static_cast<uint64_t>(xstage >> 4);
       uint64_t wd = wdesc0, xd = xdesc0;                    // descriptors of the current slot pair
       uint32_t ws = 0, wph = 0, xs = 0, xph = 0, ait = 0;   // slot PAIRS and their phases
-      const uint32_t nWp = static_cast<uint32_t>(nW) >> 1, nXp = static_cast<uint32_t>(nX) >> 1;
+      const uint32_t nWp = static_cast<uint32_t>(nW / grp), nXp = static_cast<uint32_t>(nX / grp);
       const uint32_t nacc = static_cast<uint32_t>(p.N);
 #pragma unroll 1
       for (int l = 0; l < p.L; ++l) {
@@ -825,8 +826,8 @@ __global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const __grid_c
           int seg_left = 0;         // units left in the current segment (0: the next unit opens one)
           uint32_t buf = 0;
 #pragma unroll 1
-          for (int n = sc.n; n > 0; n -= 2) {
-            const bool two = n > 1;
+          for (int n = sc.n; n > 0; n -= grp) {
+            const bool two = grp == 2 && n > 1;
             // ---- segment bookkeeping of both units (a segment = the rest of a row tile or of this CTA's range)
             bool first0 = false, first1 = false;
             if (seg_left == 0) {
@@ -876,11 +877,11 @@ __global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const __grid_c
               }
               ptx::umma_commit(w_empty0 + 8u * ws);
               ptx::umma_commit(x_empty0 + 8u * xs);
-              if (n <= 2) MEGA_RSTAMP(l, kind * 8 + 3);
+              if (n <= grp) MEGA_RSTAMP(l, kind * 8 + 3);
             }
             __syncwarp();
-            wd += 2 * wstep;
-            xd += 2 * xstep;
+            wd += grp * wstep;
+            xd += grp * xstep;
             if (++ws == nWp) { ws = 0; wph ^= 1; wd = wdesc0; }
             if (++xs == nXp) { xs = 0; xph ^= 1; xd = xdesc0; }
           }
@@ -1015,11 +1016,14 @@ int mega_launch(const MegaParams& p_in, cudaStream_t s) {
   const int total = 227 * 1024 - 1024 /*alignment*/;
   const int xstage = p.N * 128;
   const int fixed = kAttnWarps * 192 * 4 + 64 + 64 + kTblMax * 4 + 512;
-  p.nX = p.N <= 64 ? 8 : p.N <= 128 ? 4 : 2;   // even: slots are handed over in pairs
+  // ring slots are handed over in pairs (two units per full / empty barrier) while at least two X pairs fit; at
+  // 256 rows (32 KB activation tiles) the X ring holds three single tiles and every unit is handed over on its own
+  p.nX = p.N <= 64 ? 8 : p.N <= 128 ? 4 : 3;
+  p.grp = p.nX >= 4 ? 2 : 1;
   p.xring_bytes = p.nX * xstage > kVecScratch ? p.nX * xstage : kVecScratch;
   p.nW = (total - fixed - p.xring_bytes) / kWStage;
   if (p.nW > 12) p.nW = 12;
-  p.nW &= ~1;                       // slots are handed over in pairs
+  if (p.grp == 2) p.nW &= ~1;
   if (p.nW < 2) return static_cast<int>(cudaErrorInvalidValue);
   {
     const char* dbg = getenv("CCB_MEGA_DEBUG");

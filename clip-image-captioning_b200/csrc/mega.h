@@ -47,6 +47,7 @@ struct MegaParams {
   const float *lnf_g, *lnf_b;
   unsigned int* sync;          // [0] phase counter (zero at entry and at exit)
   int nW, nX, sc_cap;          // ring depths, per-warp score capacity (floats)
+  int grp;                     // units per ring hand-over (2: slot pairs, 1: single slots)
   int log2_page_tokens;
   int debug;                   // tuning only: bit 0 = skip the GEMM roles (vector phases timed alone; results are garbage)
   int xring_bytes;             // X ring size (>= 64 KB: it doubles as the scratch of the vector phases)
