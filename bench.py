@@ -53,7 +53,8 @@ def measured_traffic():
     try:
         with open(os.path.join(ROOT, "profiles", "r1_decode_mega_ncu.json")) as f:
             j = json.load(f)
-        return float(j["dram__bytes_read.sum"]) + float(j["dram__bytes_write.sum"])
+        k = j["launches"][0] if "launches" in j else j
+        return float(k["dram__bytes_read.sum"]) + float(k["dram__bytes_write.sum"])
     except Exception:
         return None
 
