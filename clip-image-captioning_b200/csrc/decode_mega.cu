@@ -114,8 +114,9 @@ struct ComputeCtx {
   uint8_t* vs;           // vector-phase scratch (generic pointer) and its shared-window address
   uint32_t vs_u32;
   float* strips;         // [8 warps][192] floats: q (scaled), k_new, v_new of the unit a warp works on
-  bool attn_prefetched;  // the K/V copies of this warp's first attention unit are already in flight
-  int u_ctx[2], u_page[2];  // cached tokens / this lane's page id of the warp's first two attention units
+  bool attn_prefetched;  // the first K/V copies of this warp's attention units are already in flight (a_* say which)
+  int a_k, a_ib, a_h, a_inflight;  // K/V stream position after the prefetch: unit ordinal, batch, batches issued / in flight
+  int u_ctx[4], u_page[4];  // cached tokens / this lane's page id of the warp's first four attention units
   unsigned long long* trace;
   int trace_it;
 };
@@ -324,9 +325,13 @@ __device__ __noinline__ void gelu_phase(const MegaParams& p, ComputeCtx& cc, int
 // keeps ptxas from serialising the loads -- in batches of 16 tokens, two batches in flight; the sum of the c_attn
 // partials is computed underneath.  lane = (token group g = lane / 8, 16-byte chunk c = lane % 8); the batches are
 // folded with an online softmax.  page_tokens is a power of two (host-checked); offsets are 32-bit element offsets.
-// prefetch_only: issue the K/V copies of this warp's first unit and return (called between the arrival at the c_attn
+// The K/V batches of ALL units of a warp form one stream with two batches in flight: when a unit has no batch left to
+// request, the freed half is refilled with the first batches of the warp's next unit, so the fold of q/k/v, the output
+// store and the unit change-over run underneath K/V copies (with several units per warp -- 128 / 256 rows -- the phase
+// is bound by these copies: 78 MB of K/V per layer at 256 rows).
+// prefetch_only: issue the first two batches of the stream and return (called between the arrival at the c_attn
 // barrier and the wait for it: cached K/V do not depend on the current step, so their latency hides behind the
-// barrier); the phase proper then skips that issue (cc.attn_prefetched).
+// barrier); the phase proper then continues from there (cc.attn_prefetched, cc.a_*).
 __device__ __noinline__ void attention_phase(const MegaParams& p, ComputeCtx& cc, int cta, int layer, const float* bias, bool prefetch_only) {
   constexpr int HD = 64;
   const int rows_out = p.g[0].rows_out, tbl_off = p.g[0].tbl_off;
@@ -348,51 +353,91 @@ __device__ __noinline__ void attention_phase(const MegaParams& p, ComputeCtx& cc
   const size_t kv_stride = static_cast<size_t>(cache.num_pages) * page_stride;
   const bf16* layer_k = cache.base + static_cast<size_t>(layer) * 2 * kv_stride;
   const uint32_t lane_dst = static_cast<uint32_t>(grp) * 128u + static_cast<uint32_t>(ch) * 16u;
-  // Context length and page ids do not change during the step: those of a warp's first two units were loaded once at
-  // kernel start (cc.u_ctx / cc.u_page); further units (more than 2 * 11 * ncta units) request theirs one unit ahead.
+  // Context length and page ids do not change during the step: those of a warp's first four units were loaded once at
+  // kernel start (cc.u_ctx / cc.u_page); further units (more than 4 * 11 * ncta units) read theirs when they come up.
   const int maxp = cache.max_pages_per_row;
-  int ctx_nx = 0, page_nx = 0, ui = 0;
-#pragma unroll 1
-  for (int unit = cw * ncta + cta; unit < total; unit += kAttnWarps * ncta, ++ui) {
-    const int b = unit / H, h = unit - b * H;
-    const int ctx = ui < 2 ? cc.u_ctx[ui] : ctx_nx;
-    const int my_page = ui < 2 ? cc.u_page[ui] : page_nx;
-    const int* bt = block_table + static_cast<uint32_t>(b) * maxp;
-    if (!prefetch_only && ui >= 1 && unit + kAttnWarps * ncta < total) {
-      const int bn = (unit + kAttnWarps * ncta) / H;
-      ctx_nx = ctx_len[bn];
-      page_nx = lane < maxp ? block_table[static_cast<uint32_t>(bn) * maxp + lane] : 0;
+  const int stride_u = kAttnWarps * ncta, unit_first = cw * ncta + cta;
+  auto unit_state = [&](int k, int unit, int& ctx, int& page) {
+    if (k < 4) {
+      ctx = k == 0 ? cc.u_ctx[0] : k == 1 ? cc.u_ctx[1] : k == 2 ? cc.u_ctx[2] : cc.u_ctx[3];
+      page = k == 0 ? cc.u_page[0] : k == 1 ? cc.u_page[1] : k == 2 ? cc.u_page[2] : cc.u_page[3];
+    } else {
+      const int bb = unit / H;
+      ctx = ctx_len[bb];
+      page = lane < maxp ? block_table[static_cast<uint32_t>(bb) * maxp + lane] : 0;
     }
-    const int npages = (ctx >> lpt) + 1;  // pages holding positions [0, ctx]
-    // page ids: held one per lane when they fit a warp (always for 16-token pages), else per-token lookups
-    const bool pages_in_warp = npages <= 32;
-    const bf16* kbase = layer_k + (static_cast<uint32_t>(h) << (lpt + 6)) + ch * 8;  // + page * page_stride + (t & ptm) * 64
-    const int nb = (ctx + 15) >> 4;
-
-    auto issue = [&](int bi) {
-      const uint32_t dst = stage_u32 + static_cast<uint32_t>(bi & 1) * 4096u + lane_dst;
+  };
+  // ---- issue side of the K/V stream
+  int i_k = 0, i_ib = 0, i_h = 0, inflight = 0;     // unit ordinal, next batch of it, real batches issued / in flight
+  int i_ctx = 0, i_page = 0, i_nb = 0;
+  bool i_valid = false, i_inwarp = true;
+  const bf16* i_kbase = layer_k;
+  const int* i_bt = block_table;
+  auto issuer_setup = [&](int k) {
+    i_k = k;
+    i_ib = 0;
+    const int unit = unit_first + k * stride_u;
+    i_valid = unit < total;
+    if (!i_valid) return;
+    unit_state(k, unit, i_ctx, i_page);
+    const int bb = unit / H, hh = unit - bb * H;
+    i_nb = (i_ctx + 15) >> 4;
+    i_inwarp = (i_ctx >> lpt) + 1 <= 32;   // page ids held one per lane when they fit a warp, else per-token lookups
+    i_kbase = layer_k + (static_cast<uint32_t>(hh) << (lpt + 6)) + ch * 8;  // + page * page_stride + (t & ptm) * 64
+    i_bt = block_table + static_cast<uint32_t>(bb) * maxp;
+  };
+  auto issue_next = [&]() {   // the next batch of the stream into the half it belongs to; always commits a group
+    while (i_valid && i_ib >= i_nb) issuer_setup(i_k + 1);
+    if (i_valid) {
+      const uint32_t dst = stage_u32 + static_cast<uint32_t>(i_h & 1) * 4096u + lane_dst;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int t = bi * 16 + i * 4 + grp;
-        const bool ok = t < ctx;
+        const int t = i_ib * 16 + i * 4 + grp;
+        const bool ok = t < i_ctx;
         const int tt = ok ? t : 0;
-        const int page = pages_in_warp ? __shfl_sync(0xffffffffu, my_page, tt >> lpt) : bt[tt >> lpt];
-        const bf16* kp = kbase + (static_cast<uint32_t>(page) * page_stride + (static_cast<uint32_t>(tt & ptm) << 6));
+        const int page = i_inwarp ? __shfl_sync(0xffffffffu, i_page, tt >> lpt) : i_bt[tt >> lpt];
+        const bf16* kp = i_kbase + (static_cast<uint32_t>(page) * page_stride + (static_cast<uint32_t>(tt & ptm) << 6));
         cp_async16(dst + i * 512u, kp, ok ? 16u : 0u);
         cp_async16(dst + i * 512u + 2048u, kp + kv_stride, ok ? 16u : 0u);
       }
-      cp_async_commit();
-    };
-    if (!cc.attn_prefetched) {
-      if (nb > 0) issue(0);
-      if (nb > 1) issue(1);
+      ++i_ib;
+      ++i_h;
+      ++inflight;
     }
+    cp_async_commit();
+  };
+  if (cc.attn_prefetched) {
+    issuer_setup(cc.a_k);
+    i_ib = cc.a_ib;
+    i_h = cc.a_h;
+    inflight = cc.a_inflight;
     cc.attn_prefetched = false;
-    if (prefetch_only) {
-      cc.attn_prefetched = true;
-      return;
-    }
+  } else {
+    issuer_setup(0);
+    issue_next();
+    issue_next();
+  }
+  if (prefetch_only) {
+    cc.attn_prefetched = true;
+    cc.a_k = i_k;
+    cc.a_ib = i_ib;
+    cc.a_h = i_h;
+    cc.a_inflight = inflight;
+    return;
+  }
+  int c_h = 0, ui = 0;   // real batches consumed, unit ordinal
+#pragma unroll 1
+  for (int unit = unit_first; unit < total; unit += stride_u, ++ui) {
+    const int b = unit / H, h = unit - b * H;
+    int ctx, my_page;
+    unit_state(ui, unit, ctx, my_page);
+    const int* bt = block_table + static_cast<uint32_t>(b) * maxp;
+    const bool pages_in_warp = (ctx >> lpt) + 1 <= 32;
+    const bf16* kbase = layer_k + (static_cast<uint32_t>(h) << (lpt + 6)) + ch * 8;
+    const int nb = (ctx + 15) >> 4;
 
+    const bool stamp_me = ui == 0 && cw == 1 && lane == 0;   // (tuning) timeline of one unit: slots 32..43 of the role stamps
+    if (stamp_me) MEGA_RSTAMP(layer, 32);
     // ---- q / k_new / v_new while the first batches are in flight: lane owns dims (2 lane, 2 lane + 1) of each
     {
       const int dim = lane * 2;
@@ -428,6 +473,7 @@ __device__ __noinline__ void attention_phase(const MegaParams& p, ComputeCtx& cc
       *reinterpret_cast<float2*>(qkvs + 2 * HD + dim) = part[2];
       __syncwarp();
     }
+    if (stamp_me) MEGA_RSTAMP(layer, 33);
     float q8[8], acc[8];
     {
       const float4 a0 = *reinterpret_cast<const float4*>(qkvs + ch * 8), a1 = *reinterpret_cast<const float4*>(qkvs + ch * 8 + 4);
@@ -458,12 +504,14 @@ __device__ __noinline__ void attention_phase(const MegaParams& p, ComputeCtx& cc
         *reinterpret_cast<uint4*>(const_cast<bf16*>(kbase) + off + (g0 ? 0 : kv_stride)) = pk;
       }
     }
+    if (stamp_me) MEGA_RSTAMP(layer, 34);
     // ---- cached tokens, 16 per batch
 #pragma unroll 1
     for (int bi = 0; bi < nb; ++bi) {
-      if (bi + 1 < nb) cp_async_wait<1>(); else cp_async_wait<0>();
+      // (groups complete in order: with two batches in flight all but the newest group is enough)
+      if (inflight >= 2) cp_async_wait<1>(); else cp_async_wait<0>();
       __syncwarp();
-      const uint32_t src = stage_u32 + static_cast<uint32_t>(bi & 1) * 4096u + lane_dst;
+      const uint32_t src = stage_u32 + static_cast<uint32_t>(c_h & 1) * 4096u + lane_dst;
       uint4 kk[4], vv[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -471,7 +519,11 @@ __device__ __noinline__ void attention_phase(const MegaParams& p, ComputeCtx& cc
         vv[i] = lds_u4(src + i * 512u + 2048u);
       }
       __syncwarp();                      // every lane has read the half: it may be refilled
-      if (bi + 2 < nb) issue(bi + 2);
+      if (stamp_me && bi < 4) MEGA_RSTAMP(layer, 35 + 2 * bi);
+      ++c_h;
+      --inflight;
+      issue_next();
+      if (stamp_me && bi < 4) MEGA_RSTAMP(layer, 36 + 2 * bi);                      // this unit's batch bi + 2, or the first batches of the warp's next unit
       float sc[4];
       float m_b = -INFINITY;
 #pragma unroll
@@ -503,6 +555,7 @@ __device__ __noinline__ void attention_phase(const MegaParams& p, ComputeCtx& cc
         acc[4] = fmaf(pr, v2.x, acc[4]); acc[5] = fmaf(pr, v2.y, acc[5]); acc[6] = fmaf(pr, v3.x, acc[6]); acc[7] = fmaf(pr, v3.y, acc[7]);
       }
     }
+    if (stamp_me) MEGA_RSTAMP(layer, 43);
     // fold the 4 token groups
     l_run += __shfl_xor_sync(0xffffffffu, l_run, 8);
     l_run += __shfl_xor_sync(0xffffffffu, l_run, 16);
@@ -531,8 +584,9 @@ __device__ __forceinline__ void init_attn_ctx(const MegaParams& p, ComputeCtx& c
   cc.vs_u32 = vs_u32;
   cc.strips = strips;
   cc.attn_prefetched = false;
+  cc.a_k = cc.a_ib = cc.a_h = cc.a_inflight = 0;
 #pragma unroll
-  for (int ui = 0; ui < 2; ++ui) {
+  for (int ui = 0; ui < 4; ++ui) {
     const int unit = (aw + kAttnWarps * ui) * p.ncta + cta;
     cc.u_ctx[ui] = 0;
     cc.u_page[ui] = 0;

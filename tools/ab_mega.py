@@ -48,7 +48,10 @@ if want_trace:
             col = col[col > 0]
             if col.numel():
                 print("  L1 %-4s %-12s med %7.2f max %7.2f min %7.2f" % (kn, rn[k], (float(col.median()) - base1) / 1e3, (float(col.max()) - base1) / 1e3, (float(col.min()) - base1) / 1e3))
+    names_a = ["enter", "qkv folded", "new token", "b0 read", "b0 issued", "b1 read", "b1 issued", "b2 read", "b2 issued", "b3 read", "b3 issued", "batches done"]
     for c in (0, 70, 147):
+        print("  CTA %3d attention unit of compute warp 1 (us after attn.wait): " % c + "  ".join("%s %.2f" % (names_a[k], (float(r[c, 32 + k]) - float(t[c, 11 + 2])) / 1e3) for k in range(12) if r[c, 32 + k] > 0))
+    for c in ():
         print("  CTA %3d fc units: x issue  " % c + " ".join("%6.2f" % ((float(v) - base1) / 1e3) if v > 0 else "   -  " for v in r[c, 44:54]))
         print("                   w ready  " + " ".join("%6.2f" % ((float(v) - base1) / 1e3) if v > 0 else "   -  " for v in r[c, 54:64]))
         print("                   x landed " + " ".join("%6.2f" % ((float(v) - base1) / 1e3) if v > 0 else "   -  " for v in r[c, 32:42]))
