@@ -1074,6 +1074,7 @@ int mega_launch(const MegaParams& p_in, cudaStream_t s) {
   // 256 rows (32 KB activation tiles) the X ring holds three single tiles and every unit is handed over on its own
   p.nX = p.N <= 64 ? 8 : p.N <= 128 ? 4 : 3;
   p.grp = p.nX >= 4 ? 2 : 1;
+  if (const char* g = getenv("CCB_MEGA_GRP")) p.grp = atoi(g) == 1 ? 1 : p.grp;   // tuning: single-slot hand-over
   p.xring_bytes = p.nX * xstage > kVecScratch ? p.nX * xstage : kVecScratch;
   p.nW = (total - fixed - p.xring_bytes) / kWStage;
   if (p.nW > 12) p.nW = 12;
