@@ -89,17 +89,20 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, di
 }
 
 
-// Tile width BN (and kernel variant) for the persistent kernels, from the B200 sweeps of tools/sweep_gemm_bn.py.  A round
-// of tiles costs k_blocks x the time of one k-block, which is bound by the SM's shared-memory port (TMA writes and MMA
-// reads of 16 KB + BN x 128 B each), i.e. proportional to 16 + BN / 8, plus a small hand-over; the number of rounds is
-// ceil(tiles / SMs).  The widest candidate wins ties.  The CTA-pair kernel (256-token tiles, half the W bytes per SM)
-// measured within +-3 % of the single-CTA kernel everywhere and ahead of it only for long K, where it is used.
+// Kernel variant and tile width BN for the persistent kernels, from the B200 sweeps of tools/sweep_gemm_bn.py.
+//  * single CTA (128-token tiles): a round of tiles costs k_blocks x the time of one k-block, which is bound by the
+//    SM's shared-memory port (TMA writes and MMA reads of 16 KB + BN x 128 B each), i.e. proportional to 16 + BN / 8,
+//    plus a small hand-over; rounds = ceil(tiles / SMs); the widest candidate wins ties.
+//  * CTA pair (256-token tiles, half the W bytes per SM): a round costs ~max(26, 3 BN / 16) in the same units (MMA
+//    bound, with a floor), rounds = ceil(tiles / pairs); it is ahead once the problem runs three or more rounds of
+//    long-enough tiles (K >= 1280) or K is very long, and behind on one- or two-round problems (cluster launch and
+//    synchronisation, no overlap to win back).
 void pick_persist(int tokens, int features, int k_blocks, int num_sms, int force_orientation, int force_bn, bool* pair_out,
                   int* bn_out) {
   const int m_tiles = (tokens + 127) / 128;
-  long long best = 0;
+  long long best = 0, best_rounds = 0;
   int best_bn = 0;
-  for (int bn = 256; bn >= 64; bn -= 32) {
+  for (int bn = 256; bn >= (force_bn ? 32 : 64); bn -= 32) {
     if (force_bn && bn != force_bn) continue;
     const long long tiles = static_cast<long long>(m_tiles) * ((features + bn - 1) / bn);
     const long long rounds = (tiles + num_sms - 1) / num_sms;
@@ -107,11 +110,28 @@ void pick_persist(int tokens, int features, int k_blocks, int num_sms, int force
     if (best_bn == 0 || cost < best) {
       best = cost;
       best_bn = bn;
+      best_rounds = rounds;
     }
   }
-  *bn_out = best_bn;
-  *pair_out = force_orientation == 3 || (force_orientation != 4 && best_bn == 256 && k_blocks >= 64 && tokens >= 512 &&
-                                         ((tokens + 255) / 256) * ((features + 255) / 256) <= num_sms / 2);
+  bool pair = force_orientation == 3;
+  if (force_orientation != 3 && force_orientation != 4)
+    pair = tokens >= 512 && (k_blocks >= 64 || (best_rounds >= 3 && k_blocks >= 20));
+  if (pair && !force_bn) {
+    const int m2 = (tokens + 255) / 256, pairs = num_sms / 2;
+    long long pbest = 0;
+    for (int bn = 256; bn >= 64; bn -= 32) {
+      const long long tiles = static_cast<long long>(m2) * ((features + bn - 1) / bn);
+      const long long rounds = (tiles + pairs - 1) / pairs;
+      const long long per = 3 * bn / 16 > 26 ? 3 * bn / 16 : 26;
+      const long long cost = rounds * per * 64 + bn;   // (+ bn: the narrower tile wins ties)
+      if (bn == 256 || cost < pbest) {
+        pbest = cost;
+        best_bn = bn;
+      }
+    }
+  }
+  *bn_out = best_bn ? best_bn : force_bn;
+  *pair_out = pair;
 }
 
 int launch_persist(const GemmArgs& a, const GemmParams& p_in, int bn, bool pair, int num_sms, cudaStream_t s) {
@@ -252,9 +272,9 @@ int gemm_launch(const GemmArgs& a, const GemmWorkspace& w, cudaStream_t stream) 
   }
 
   if (persist) {
-    bool pair = a.force_orientation == 3;
-    int pbn = a.force_bn;
-    if (a.force_orientation < 3 || pbn == 0) pick_persist(a.tokens, a.features, p.k_blocks, w.num_sms, a.force_orientation, a.force_bn, &pair, &pbn);
+    bool pair = false;
+    int pbn = 0;
+    pick_persist(a.tokens, a.features, p.k_blocks, w.num_sms, a.force_orientation, a.force_bn, &pair, &pbn);
     if (pbn < 32 || pbn > 256 || pbn % 32) return fail("unsupported BN for the persistent GEMM");
     return launch_persist(a, p, pbn, pair, w.num_sms, stream);
   }

@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) gemm_pair_kernel(const __g
 
   if (warp == 0 || warp == 6) {
     // ------------------------------------------------------------ TMA producers (both CTAs): warp 0 loads X, warp 6 W
-    if (lane == 0) {
+    {
       const bool is_x = warp == 0;
       if (is_x) ptx::grid_dep_wait();
       const CUtensorMap* tm = is_x ? &tma_x : &tma_w;
@@ -267,50 +267,59 @@ __global__ void __launch_bounds__(kPersistThreads, 1) gemm_pair_kernel(const __g
       const uint64_t hint = is_x ? ptx::kEvictLast : ptx::kEvictNormal;
       const uint32_t lfull0 = ptx::mapa_shared(full0, 0);   // the leader's `full` barriers
       uint32_t s = 0, ph = 0;
+#pragma unroll 1
       for (int tile = pair; tile < ntiles; tile += npairs) {
         const int row = is_x ? (tile % pp.m_tiles) * 256 + static_cast<int>(rank) * 128
                              : (tile / pp.m_tiles) * BN + static_cast<int>(rank) * (BN >> 1);
+#pragma unroll 1
         for (int kb = 0; kb < nkb; ++kb) {
           ptx::mbar_wait(empty0 + 8u * s, ph ^ 1);
-          if (pp.debug & 1) {   // tuning: no TMA loads
-            if (is_x && leader) ptx::mbar_arrive(full0 + 8u * s);
-          } else {
-            if (is_x && leader) ptx::mbar_arrive_expect_tx(full0 + 8u * s, 2u * stage_bytes);
-            ptx::tma_load_2d_pair(smem_base + s * stage_bytes + off, tm, lfull0 + 8u * s, kb * 64, row, hint);
+          if (ptx::elect_one()) {
+            if (pp.debug & 1) {   // tuning: no TMA loads
+              if (is_x && leader) ptx::mbar_arrive(full0 + 8u * s);
+            } else {
+              if (is_x && leader) ptx::mbar_arrive_expect_tx(full0 + 8u * s, 2u * stage_bytes);
+              ptx::tma_load_2d_pair(smem_base + s * stage_bytes + off, tm, lfull0 + 8u * s, kb * 64, row, hint);
+            }
           }
+          __syncwarp();
           if (++s == static_cast<uint32_t>(S)) { s = 0; ph ^= 1; }
         }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer (leader only)
-    if (leader && lane == 0) {
+    // ------------------------------------------------------------ MMA issuer (leader only; converged warp, elected issue)
+    if (leader) {
       const uint32_t idesc = ptx::umma_idesc_bf16(256, BN);
+      const uint64_t desc0 = ptx::umma_desc_k_sw128(smem_base);
       uint32_t s = 0, ph = 0, it = 0;
+#pragma unroll 1
       for (int tile = pair; tile < ntiles; tile += npairs, ++it) {
         const uint32_t buf = it & 1, aph = (it >> 1) & 1;
         ptx::mbar_wait(tempty0 + 8u * buf, aph ^ 1);
         ptx::tc_fence_after();
         const uint32_t tacc = tmem_base + buf * 256u;
+#pragma unroll 1
         for (int kb = 0; kb < nkb; ++kb) {
           ptx::mbar_wait(full0 + 8u * s, ph);
           ptx::tc_fence_after();
-          const uint32_t sa = smem_base + s * stage_bytes;
-          const uint64_t adesc = ptx::umma_desc_k_sw128(sa);
-          const uint64_t bdesc = ptx::umma_desc_k_sw128(sa + 128u * 128u);
-          if ((pp.debug & 2) == 0) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              ptx::umma_bf16_pair(tacc, adesc + 2u * k, bdesc + 2u * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          if (ptx::elect_one()) {
+            const uint64_t adesc = desc0 + static_cast<uint64_t>((s * stage_bytes) >> 4);
+            const uint64_t bdesc = adesc + static_cast<uint64_t>((128u * 128u) >> 4);
+            if ((pp.debug & 2) == 0) {
+              ptx::umma_bf16_pair(tacc, adesc, bdesc, idesc, kb > 0 ? 1u : 0u);
+              ptx::umma_bf16_pair(tacc, adesc + 2u, bdesc + 2u, idesc, 1u);
+              ptx::umma_bf16_pair(tacc, adesc + 4u, bdesc + 4u, idesc, 1u);
+              ptx::umma_bf16_pair(tacc, adesc + 6u, bdesc + 6u, idesc, 1u);
+            }
+            ptx::umma_commit_pair(empty0 + 8u * s, 3);
+            if (kb == nkb - 1) ptx::umma_commit_pair(tfull0 + 8u * buf, 3);
           }
-          ptx::umma_commit_pair(empty0 + 8u * s, 3);
+          __syncwarp();
           if (++s == static_cast<uint32_t>(S)) { s = 0; ph ^= 1; }
         }
-        ptx::umma_commit_pair(tfull0 + 8u * buf, 3);
       }
     }
-    __syncwarp();
   } else {
     // ------------------------------------------------------------ epilogue warps (both CTAs, own 128 token rows)
     ptx::grid_dep_wait();
