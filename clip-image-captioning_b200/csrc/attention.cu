@@ -171,6 +171,8 @@ __global__ void __launch_bounds__(256) attention_prefill_mma_kernel(
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const bf16* base = qkv + static_cast<size_t>(b) * S * 3 * d;
+  ptx::grid_dep_wait();     // qkv comes from the c_attn GEMM this kernel is chained behind (PDL)
+  ptx::grid_dep_launch();
 
   // ---- stage K / V (16-byte chunks, zero padded), append them to the KV cache, build the key mask
   const int cpr = HDP / 8;                // chunks per staged row
@@ -329,9 +331,8 @@ int launch_prefill_mma(const bf16* qkv, bf16* out, int B, int S, int H, int hd, 
     configured = smem;
   }
   const int warps = (S + 15) / 16;
-  attention_prefill_mma_kernel<NT, KS><<<dim3(H, B), warps * 32, smem, s>>>(qkv, out, S, H, hd, scale, causal, c, layer,
-                                                                           block_table, pos0, write_cache, key_mask);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_kernel(attention_prefill_mma_kernel<NT, KS>, dim3(H, B), dim3(warps * 32), smem, s, true, qkv, out, S, H, hd,
+                                scale, causal, c, layer, block_table, pos0, write_cache, key_mask);
   return e == cudaSuccess ? 0 : (int)e;
 }
 

@@ -63,6 +63,53 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   }
 }
 
+// One WARP per row, the row held in registers (NV float4 per lane): no shared memory, no block barrier, all loads of
+// a row in flight at once.  With thousands of rows (ViT / mapper / prefill) the one-CTA-per-row kernel above is a chain
+// of two block reductions per CTA and runs in waves; here every row of the call is resident at once.
+template <int NV>
+__global__ void __launch_bounds__(256) layernorm_rows_kernel(const float* __restrict__ x, long long ldx,
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                             float eps, bf16* __restrict__ y, long long ldy, int rows, int d) {
+  ptx::grid_dep_wait();
+  ptx::grid_dep_launch();
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int nq = d >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(r) * ldx);
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int q = lane + 32 * i;
+    v[i] = q < nq ? xr[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mean = warp_sum(s) / d;
+  float qs = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    if (lane + 32 * i < nq) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
+      qs += (a * a + b * b) + (c * c + e * e);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(qs) / d + eps);
+  uint2* yr = reinterpret_cast<uint2*>(y + static_cast<long long>(r) * ldy);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int q = lane + 32 * i;
+    if (q < nq) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + q);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + q);
+      uint2 pk;
+      pk.x = pack_bf16x2((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y);
+      pk.y = pack_bf16x2((v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
+      yr[q] = pk;
+    }
+  }
+}
+
 // ---------------------------------------------------------------- ViT patchify (im2col for stride == kernel)
 template <typename InT>
 __device__ __forceinline__ float to_f32(InT v);
@@ -292,10 +339,21 @@ int layernorm_f32_bf16(const float* x, long long ldx, const float* gamma, const 
                        long long ldy, int rows, int d, cudaStream_t s) {
   if (rows <= 0) return 0;
   if (d % 4 || ldx % 4 || ldy % 4) return (int)cudaErrorInvalidValue;
-  {
-    cudaError_t e = launch_kernel(layernorm_kernel<bf16>, dim3(rows), dim3(256), d * sizeof(float), s, true, x, ldx, gamma, beta, eps, y, ldy, d);
-    if (e != cudaSuccess) return (int)e;
+  cudaError_t e;
+  const int nq = d / 4;
+  if (rows >= 256 && nq <= 32 * 32) {
+    // many rows: one warp per row, 8 rows per CTA
+    const dim3 grid((rows + 7) / 8), block(256);
+    if (nq <= 32 * 8)
+      e = launch_kernel(layernorm_rows_kernel<8>, grid, block, 0, s, true, x, ldx, gamma, beta, eps, y, ldy, rows, d);
+    else if (nq <= 32 * 16)
+      e = launch_kernel(layernorm_rows_kernel<16>, grid, block, 0, s, true, x, ldx, gamma, beta, eps, y, ldy, rows, d);
+    else
+      e = launch_kernel(layernorm_rows_kernel<32>, grid, block, 0, s, true, x, ldx, gamma, beta, eps, y, ldy, rows, d);
+  } else {
+    e = launch_kernel(layernorm_kernel<bf16>, dim3(rows), dim3(256), d * sizeof(float), s, true, x, ldx, gamma, beta, eps, y, ldy, d);
   }
+  if (e != cudaSuccess) return (int)e;
   return 0;
 }
 int layernorm_f32_f32(const float* x, long long ldx, const float* gamma, const float* beta, float eps, float* y,
