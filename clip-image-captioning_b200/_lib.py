@@ -32,7 +32,7 @@ class GenParams(C.Structure):
         ("eos_token", C.c_int32), ("temperature", C.c_float), ("top_p", C.c_float), ("top_k", C.c_int32),
         ("repetition_penalty", C.c_float), ("beam_size", C.c_int32), ("seed", C.c_uint64),
         ("q_noise", C.c_void_p), ("q_ld", C.c_int64), ("row_ids", C.c_void_p), ("top_p_rows", C.c_void_p),
-        ("top_k_rows", C.c_void_p)]
+        ("top_k_rows", C.c_void_p), ("typ_p", C.c_float), ("typ_p_rows", C.c_void_p)]
 
 
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float

@@ -420,6 +420,8 @@ SampleParams sample_params(ccb_ctx* c, const ccb_gen_params* p, int rows) {
   sp.top_k = p->top_k;
   sp.top_p_rows = p->top_p_rows;
   sp.top_k_rows = p->top_k_rows;
+  sp.typ_p = p->typ_p;
+  sp.typ_p_rows = p->typ_p_rows;
   sp.repetition_penalty = p->repetition_penalty;
   sp.q_noise = p->q_noise;
   sp.ldq = p->q_ld;
@@ -471,11 +473,12 @@ int decode_iteration(ccb_ctx* c, const ccb_gen_params* p, int N, int rows, int T
 
 std::string graph_key(const ccb_gen_params* p, int N, int rows, int T, int c_mega) {
   char buf[512];
-  snprintf(buf, sizeof(buf), "g%d m%d N%d r%d T%d st%d ms%d eos%d t%a p%a k%d rp%a b%d seed%llu q%p ld%lld ids%p pr%p kr%p",
+  snprintf(buf, sizeof(buf), "g%d m%d N%d r%d T%d st%d ms%d eos%d t%a p%a k%d rp%a b%d seed%llu q%p ld%lld ids%p pr%p kr%p ty%a tr%p",
            c_mega, p->mode, N, rows, T, p->stop_token, p->max_stops, p->eos_token, p->temperature, p->top_p, p->top_k,
            p->repetition_penalty, p->beam_size, static_cast<unsigned long long>(p->seed),
            static_cast<const void*>(p->q_noise), static_cast<long long>(p->q_ld), static_cast<const void*>(p->row_ids),
-           static_cast<const void*>(p->top_p_rows), static_cast<const void*>(p->top_k_rows));
+           static_cast<const void*>(p->top_p_rows), static_cast<const void*>(p->top_k_rows), p->typ_p,
+           static_cast<const void*>(p->typ_p_rows));
   return buf;
 }
 

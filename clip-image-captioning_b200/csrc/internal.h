@@ -134,7 +134,7 @@ struct SamplerScratch {
 // greedy: next[b] = argmax_v logits[b, v] (lowest index wins ties)
 int sample_greedy(const float* logits, long long ld, int B, int V, int* next, cudaStream_t s);
 // nucleus / top-k sampling following sampling.py:114-162 + multinomial (== argmax(p / q), q ~ Exp(1)):
-//   logits <- repetition penalty over history (optional) -> / temperature -> top-k -> top-p -> softmax -> sample
+//   logits <- repetition penalty over history (optional) -> / temperature -> top-k -> top-p -> typical-p -> softmax -> sample
 // top_p / top_k may be per-row device arrays (or null -> scalar). q_noise [B, ldq] f32 Exp(1) samples or null
 // -> in-kernel Philox keyed by (seed, row_id[b], step).
 struct SampleParams {
@@ -143,6 +143,8 @@ struct SampleParams {
   int top_k = 0;
   const float* top_p_rows = nullptr;
   const int* top_k_rows = nullptr;
+  float typ_p = 0.f;                   // typical decoding budget (sampling.py:72-102); <= 0 disables
+  const float* typ_p_rows = nullptr;   // per-row budgets: the filter then runs on every row (reference: any(typ_p > 0))
   float repetition_penalty = 1.f;
   const int* history = nullptr;  // [B, ld_hist] tokens generated so far
   long long ld_hist = 0;

@@ -133,7 +133,9 @@ __global__ void __launch_bounds__(kSampThreads) greedy_kernel(const float* __res
 // ------------------------------------------------------------------------------------------------ top-k / top-p
 // 4-bit radix select over the order keys of vals[0..V).  mode 0: k-th largest (by count, 1-based `kth`).
 // mode 1: first element (descending) at which the cumulative probability mass exceeds top_p, where the mass of
-// element i is expf(vals[i] - vmax) * inv_sum.  Returns through shared scalars:
+// element i is expf(vals[i] - vmax) * inv_sum.  mode 2 (typical decoding, sampling.py:72-102): the elements are ordered by
+// ASCENDING |log p_i + H| (log p_i = vals[i] - vmax - lse, H the entropy) and the boundary is the first element at which
+// the cumulative probability is no longer below top_p.  Returns through shared scalars:
 //   sel_key  : key of the boundary element (0 when the target is never reached -> keep everything)
 //   mass_gt  : mode 1: mass strictly above the boundary key;   cnt_eq: elements equal to the boundary key
 struct SelectResult {
@@ -143,8 +145,13 @@ struct SelectResult {
   int reached;
 };
 
+__device__ __forceinline__ uint32_t typical_key(float x, float vmax, float lse, float ent) {
+  return order_key(-fabsf(((x - vmax) - lse) + ent));   // descending key order == ascending distance to the entropy
+}
+
 __device__ SelectResult radix_select(const float* vals, int V, int mode, int kth, float top_p, float vmax,
-                                     float inv_sum, double* dscratch /*32 + 16*/, int* iscratch /*32 + 16*/) {
+                                     float inv_sum, double* dscratch /*32 + 16*/, int* iscratch /*32 + 16*/,
+                                     float lse = 0.f, float ent = 0.f) {
   uint32_t prefix = 0;
   double mass_above = 0.0;
   int cnt_above = 0;
@@ -163,12 +170,13 @@ __device__ SelectResult radix_select(const float* vals, int V, int mode, int kth
     }
     for (int v = threadIdx.x; v < V; v += blockDim.x) {
       const float x = vals[v];
-      const uint32_t key = order_key(x);
+      const uint32_t key = mode == 2 ? typical_key(x, vmax, lse, ent) : order_key(x);
       const bool match = (nib == 7) || ((key >> (shift + 4)) == (prefix >> (shift + 4)));
       if (match) {
         const int b = (key >> shift) & 15;
         double pm = 0.0;
         if (mode == 1) pm = static_cast<double>(expf(x - vmax) * inv_sum);
+        if (mode == 2) pm = static_cast<double>(expf((x - vmax) - lse));
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
           if (q == b) {
@@ -182,7 +190,7 @@ __device__ SelectResult radix_select(const float* vals, int V, int mode, int kth
     for (int b = 0; b < 16; ++b) {
       const int cb = block_sum_i(c[b], iscratch);
       double mb = 0.0;
-      if (mode == 1) mb = block_sum_d(m[b], dscratch);
+      if (mode != 0) mb = block_sum_d(m[b], dscratch);
       if (threadIdx.x == 0) {
         bin_cnt[b] = cb;
         bin_mass[b] = mb;
@@ -196,8 +204,10 @@ __device__ SelectResult radix_select(const float* vals, int V, int mode, int kth
       bool hit;
       if (mode == 0)
         hit = (cnt_above + bin_cnt[b] >= kth);
-      else
+      else if (mode == 1)
         hit = (static_cast<float>(mass_above + bin_mass[b]) > top_p);
+      else
+        hit = !(static_cast<float>(mass_above + bin_mass[b]) < top_p);
       if (hit) {
         chosen = b;
         break;
@@ -231,6 +241,8 @@ struct TopPArgs {
   int top_k;
   const float* top_p_rows;
   const int* top_k_rows;
+  float typ_p;
+  const float* typ_p_rows;
   float rep_pen;
   const int* history;
   long long ld_hist;
@@ -348,6 +360,29 @@ __global__ void __launch_bounds__(kSampThreads) top_p_kernel(const TopPArgs a) {
           }
         }
       }
+      __syncthreads();
+    }
+  }
+  // ---- typical filtering (sampling.py:72-102), on the row as filtered so far (sampling.py:205-206)
+  const float typ_p = a.typ_p_rows ? a.typ_p_rows[b] : a.typ_p;
+  if (a.typ_p_rows != nullptr || typ_p > 0.f) {
+    float s2 = 0.f;
+    for (int v = threadIdx.x; v < V; v += blockDim.x) s2 += expf(vals[v] - mx);
+    s2 = block_sum(s2, fscratch);
+    const float lse = logf(s2);
+    float e = 0.f;
+    for (int v = threadIdx.x; v < V; v += blockDim.x) {
+      const float x = vals[v];
+      if (x != -INFINITY) {
+        const float lp = (x - mx) - lse;
+        e += lp * expf(lp);
+      }
+    }
+    const float ent = -block_sum(e, fscratch);
+    const SelectResult r = radix_select(vals, V, 2, 0, typ_p, mx, 0.f, dscratch, iscratch, lse, ent);
+    if (r.reached) {
+      for (int v = threadIdx.x; v < V; v += blockDim.x)
+        if (typical_key(vals[v], mx, lse, ent) < r.key) vals[v] = -INFINITY;
       __syncthreads();
     }
   }
@@ -667,6 +702,7 @@ int sample_top_p(const float* logits, long long ld, int B, int V, const SamplePa
   a.logits = logits; a.ld = ld; a.V = V;
   a.temperature = sp.temperature; a.top_p = sp.top_p; a.top_k = sp.top_k;
   a.top_p_rows = sp.top_p_rows; a.top_k_rows = sp.top_k_rows;
+  a.typ_p = sp.typ_p; a.typ_p_rows = sp.typ_p_rows;
   a.rep_pen = sp.repetition_penalty; a.history = sp.history; a.ld_hist = sp.ld_hist;
   a.hist_len = sp.hist_len; a.hist_len_scalar = sp.hist_len_scalar; a.hist_len_from_step = sp.hist_len_from_step;
   a.q_noise = sp.q_noise; a.ldq = sp.ldq; a.q_step_stride = sp.q_step_stride; a.seed = sp.seed; a.row_ids = sp.row_ids;

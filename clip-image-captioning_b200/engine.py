@@ -217,12 +217,14 @@ class Engine:
                    temperature: float = 1.0, top_p: float = 0.0, top_k: int = 0, repetition_penalty: float = 1.0,
                    beam_size: int = 1, seed: int = 0, q_noise: Optional[torch.Tensor] = None,
                    row_ids: Optional[torch.Tensor] = None, top_p_rows: Optional[torch.Tensor] = None,
-                   top_k_rows: Optional[torch.Tensor] = None):
+                   top_k_rows: Optional[torch.Tensor] = None, typ_p: float = 0.0,
+                   typ_p_rows: Optional[torch.Tensor] = None):
         p = GenParams()
         p.mode = {"greedy": _lib.GEN_GREEDY, "sample": _lib.GEN_SAMPLE, "beam": _lib.GEN_BEAM}[mode]
         p.max_new_tokens, p.stop_token, p.max_stops, p.eos_token = max_new_tokens, stop_token, max_stops, eos_token
         p.temperature, p.top_p, p.top_k, p.repetition_penalty = temperature, top_p, top_k, repetition_penalty
         p.beam_size, p.seed = beam_size, seed
+        p.typ_p = typ_p
         keep = []
         if q_noise is not None:
             q_noise = self._dev(q_noise, torch.float32)
@@ -240,6 +242,10 @@ class Engine:
             top_k_rows = self._dev(top_k_rows, torch.int32)
             p.top_k_rows = top_k_rows.data_ptr()
             keep.append(top_k_rows)
+        if typ_p_rows is not None:
+            typ_p_rows = self._dev(typ_p_rows, torch.float32)
+            p.typ_p_rows = typ_p_rows.data_ptr()
+            keep.append(typ_p_rows)
         p._keep = keep
         return p
 

@@ -1,4 +1,4 @@
-"""Batched logit processors with the reference's signatures (sampling.py:65-69, 114-162), executed by the fused
+"""Batched logit processors with the reference's signatures (sampling.py:65-69, 72-102, 114-162), executed by the fused
 sampler kernel on the device.  They return NEW tensors (the reference mutates / masked_fills)."""
 from typing import Optional, Union
 
@@ -60,3 +60,30 @@ def top_k_top_p_filtering_batch(logits: torch.Tensor, top_k: Union[int, float, t
 def top_k_top_p_filtering(logits, top_k=0, top_p=0.0, filter_value=-float("inf"), engine: Engine = None):
     """inference.py:24-51 / evaluate_model.py:67-94 (1-D)."""
     return top_k_top_p_filtering_batch(logits, top_k=int(top_k), top_p=float(top_p), filter_value=filter_value, engine=engine)
+
+
+def typical_filtering(logits: torch.Tensor, typ_p: Union[float, torch.Tensor] = 0.25, min_tokens_to_keep: int = 1,
+                      filter_value=float("-inf"), engine: Engine = None):
+    """sampling.py:72-102 (typical decoding): keep the tokens whose information content is closest to the entropy until
+    their mass reaches typ_p (float or per-row tensor).  A tensor with no positive entry leaves the logits untouched, a
+    tensor with some positive entry filters every row, as in the reference."""
+    if filter_value != float("-inf"):
+        raise ValueError("only filter_value=-inf is supported")
+    if min_tokens_to_keep > 1:
+        raise ValueError("min_tokens_to_keep > 1 is not supported (the reference never passes it)")
+    eng = _engine_of(logits, engine)
+    kw = {}
+    if torch.is_tensor(typ_p):
+        if not bool(torch.any(typ_p > 0)):
+            return logits.clone()
+        kw["typ_p_rows"] = typ_p.reshape(-1).float()
+    elif typ_p > 0.0:
+        kw["typ_p"] = float(typ_p)
+    else:
+        return logits.clone()
+    squeeze = logits.dim() == 1
+    L = logits.unsqueeze(0) if squeeze else logits
+    p = eng.gen_params("sample", 1, q_noise=torch.ones(1, L.shape[1]), **kw)
+    p.q_ld = 0
+    out = eng.sample(L, p, return_filtered=True)[1]
+    return out[0] if squeeze else out

@@ -74,6 +74,10 @@ typedef struct ccb_gen_params {
   const int64_t* row_ids;    /* optional global image ids [N] keying the Philox stream (multi-GPU invariance) */
   const float* top_p_rows;   /* optional per-row top_p [N] (sampling.py:146-148) */
   const int32_t* top_k_rows; /* optional per-row top_k [N] (sampling.py:135-145) */
+  float typ_p;               /* typical decoding budget (sampling.py:72-102, applied after top-k / top-p as in
+                                sampling.py:205-206); <= 0 disables */
+  const float* typ_p_rows;   /* optional per-row budgets [N]: the filter then runs on every row, as the reference does
+                                when any(typ_p > 0) */
 } ccb_gen_params;
 
 /* ---- lifetime ------------------------------------------------------------------------------------------ */

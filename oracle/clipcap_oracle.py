@@ -301,6 +301,31 @@ def top_k_top_p_filtering_batch(logits, top_k=0, top_p=0.0, filter_value=float("
     return logits
 
 
+def typical_filtering(logits, typ_p=0.25, min_tokens_to_keep=1, filter_value=float("-inf")):
+    """sampling.py:72-102 (typical decoding, Meister et al.): keep the tokens whose information content is closest to
+    the entropy of the (already filtered) distribution until their mass reaches typ_p; ties at the cutoff survive.
+    typ_p float or per-row tensor [B] / [B, 1]; rows with typ_p <= 0 are only touched when some row is > 0, exactly as
+    the reference (a zero budget keeps the single most typical value)."""
+    if (type(typ_p) == float and typ_p > 0.0) or (torch.is_tensor(typ_p) and torch.any(typ_p > 0)):
+        if torch.is_tensor(typ_p) and typ_p.size(-1) != 1:
+            typ_p = typ_p.unsqueeze(-1)
+        normalized = F.log_softmax(logits, dim=-1)
+        p = normalized.exp()
+        entropy = -torch.nansum(normalized * p, dim=-1, keepdim=True)
+        shifted_scores = torch.abs(normalized + entropy)
+        sorted_scores, sorted_indices = torch.sort(shifted_scores, descending=False, dim=-1, stable=True)
+        sorted_p = p.gather(dim=-1, index=sorted_indices)
+        cumulative_probs = torch.cumsum(sorted_p, dim=-1)
+        last_ind = torch.sum(cumulative_probs < typ_p, dim=-1, keepdim=True)
+        last_ind = last_ind.clamp_max(logits.size(-1) - 1)   # (the reference indexes out of range when the mass is never reached)
+        remove = sorted_scores > sorted_scores.gather(dim=-1, index=last_ind)
+        if min_tokens_to_keep > 1:
+            remove[:, :min_tokens_to_keep] = False
+        remove = remove.scatter(dim=-1, index=sorted_indices, src=remove)
+        logits = logits.masked_fill(remove, filter_value)
+    return logits
+
+
 def multinomial_from_noise(probs: torch.Tensor, q: torch.Tensor, n: int = 1) -> torch.Tensor:
     """torch.multinomial(p, n, replacement=False) == topk(p / q, n) with q ~ Exp(1) drawn by
     `empty_like(p).exponential_(1, generator)` (ATen multinomial kernel; verified against torch.multinomial in

@@ -258,3 +258,29 @@ def test_philox_sampler_is_deterministic_and_row_keyed(tiny_engine, sx):
     perm = torch.tensor([3, 0, 5, 1, 4, 2])
     c = eng.sample(L[perm], eng.gen_params("sample", 1, top_p=0.9, seed=5, row_ids=ids[perm]))[0].cpu()
     assert torch.equal(c, a[perm])
+
+
+def test_typical_filtering_matches_reference(tiny_engine):
+    """sampling.typical_filtering (sampling.py:72-102) through the fused sampler kernel vs the reference-generated fixture
+    and the oracle: scalar and per-row budgets, and behind the nucleus filter (the order of sampling.generate)."""
+    from clipcap_b200 import sampling as S
+    tx = torch.load(os.path.join(GOLDEN, "typical.pt"), weights_only=False)
+    L = tx["logits"]
+
+    def close_sets(got, want):
+        # the entropy is an fp32 sum whose order differs from ATen's: a token exactly at the cutoff may flip; everything
+        # else (kept values bit-identical, removed = -inf) must agree
+        got = got.cpu()
+        if same(got, want):
+            return True
+        diff = torch.isinf(got) != torch.isinf(want)
+        return int(diff.sum()) <= 1 and torch.equal(got[~diff & ~torch.isinf(want)], want[~diff & ~torch.isinf(want)])
+
+    for tp in (0.2, 0.5, 0.9):
+        assert close_sets(S.typical_filtering(L, tp, engine=tiny_engine), tx["typ_%s" % tp]), tp
+        assert close_sets(S.typical_filtering(L, tp, engine=tiny_engine), orc.typical_filtering(L, tp)), tp
+    assert close_sets(S.typical_filtering(L, tx["typ_rows_p"].clone(), engine=tiny_engine), tx["typ_rows"])
+    p = tiny_engine.gen_params("sample", 1, q_noise=torch.ones_like(L), top_p=0.9, typ_p=0.5)
+    assert close_sets(tiny_engine.sample(L, p, return_filtered=True)[1], tx["topp_0.9_typ_0.5"])
+    assert torch.equal(S.typical_filtering(L, 0.0, engine=tiny_engine), L)
+    assert torch.equal(S.typical_filtering(L, torch.zeros(L.shape[0]), engine=tiny_engine), L)

@@ -157,3 +157,14 @@ def test_multinomial_identity(sx):
     q2 = torch.empty_like(probs).exponential_(1, generator=g)
     assert torch.equal(orc.multinomial_from_noise(probs, q1, 1), sx["multinomial_1"])
     assert torch.equal(orc.multinomial_from_noise(probs, q2, 2), sx["multinomial_2"])
+
+
+def test_typical_filtering_matches_reference():
+    """sampling.py:72-102 on raw logits, per-row budgets and behind the nucleus filter (order of sampling.generate)."""
+    tx = torch.load(os.path.join(GOLDEN, "typical.pt"), weights_only=False)
+    L = tx["logits"]
+    for tp in (0.2, 0.5, 0.9):
+        assert same(orc.typical_filtering(L, tp), tx["typ_%s" % tp]), tp
+    assert same(orc.typical_filtering(L, tx["typ_rows_p"].clone()), tx["typ_rows"])
+    assert same(orc.typical_filtering(orc.top_k_top_p_filtering_batch(L, 0, 0.9), 0.5), tx["topp_0.9_typ_0.5"])
+    assert torch.equal(orc.typical_filtering(L, 0.0), L)          # disabled

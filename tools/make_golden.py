@@ -211,18 +211,42 @@ def make_sampler_fixture(ref, seed):
     return fx
 
 
+def make_typical_fixture(ref, seed):
+    """sampling.typical_filtering (sampling.py:72-102) on raw, top-p filtered and per-row budgets."""
+    torch.manual_seed(seed)
+    B, V = 6, 1031
+    logits = torch.randn(B, V) * 3.0
+    logits[3] = logits[3] * 0.2                                       # a flat row (high entropy)
+    logits[4] = torch.round(logits[4])                                # many ties
+    fx = {"logits": logits}
+    f = ref.sampling.typical_filtering
+    for tp in (0.2, 0.5, 0.9):
+        fx["typ_%s" % tp] = f(logits.clone(), typ_p=tp)
+    rows = torch.tensor([0.1, 0.25, 0.5, 0.75, 0.9, 0.95])
+    fx["typ_rows_p"] = rows
+    fx["typ_rows"] = f(logits.clone(), typ_p=rows.clone())
+    nucleus = ref.sampling.top_k_top_p_filtering_batch(logits.clone(), top_k=0, top_p=0.9)
+    fx["topp_0.9_typ_0.5"] = f(nucleus.clone(), typ_p=0.5)            # the order of sampling.generate (:205-206)
+    return fx
+
+
 def main():
     ref = ref_harness.load_reference()
     os.makedirs(OUT, exist_ok=True)
-    for arch, seed in (("gpt2", 11), ("gptj", 12)):
+    for arch, seed in (() if "--only-typical" in sys.argv else (("gpt2", 11), ("gptj", 12))):
         fx = make_model_fixture(ref, arch, seed)
         path = os.path.join(OUT, "tiny_%s.pt" % arch)
         torch.save(fx, path)
         print(path, os.path.getsize(path) // 1024, "KiB", "stop_id", fx["stop_id"])
         for k in ("greedy", "beam5", "beam3_T2", "nobeam_inference", "nobeam_evaluate"):
             print("  ", k, fx[k])
-    fx = make_sampler_fixture(ref, 21)
-    path = os.path.join(OUT, "sampler.pt")
+    if "--only-typical" not in sys.argv:
+        fx = make_sampler_fixture(ref, 21)
+        path = os.path.join(OUT, "sampler.pt")
+        torch.save(fx, path)
+        print(path, os.path.getsize(path) // 1024, "KiB")
+    fx = make_typical_fixture(ref, 22)
+    path = os.path.join(OUT, "typical.pt")
     torch.save(fx, path)
     print(path, os.path.getsize(path) // 1024, "KiB")
 

@@ -14,13 +14,16 @@ __global__ void __launch_bounds__(384, 1) issue_kernel(int N, int iters, int spi
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - ptx::smem_u32(smem_raw));
   const uint32_t bars = base + 4 * 49152;   // 8 stages of 48 KB
-  const uint32_t done_bar = bars, never_bar = bars + 8, commit_bar = bars + 16, slot = bars + 64;
+  const uint32_t done_bar = bars, never_bar = bars + 8, commit_bar = bars + 16, slot = bars + 64;   // commit_bar .. +24: four barriers
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < 4 * 49152 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(gen)[i] = 0x3c003c00u + (i * 2654435761u & 0x007f007fu);
   if (threadIdx.x == 0) {
     ptx::mbar_init(done_bar, 1);
     ptx::mbar_init(never_bar, 1);
     ptx::mbar_init(commit_bar, 1);
+    ptx::mbar_init(commit_bar + 8, 1);
+    ptx::mbar_init(commit_bar + 16, 1);
+    ptx::mbar_init(commit_bar + 24, 1);
     ptx::fence_mbar_init();
   }
   ptx::fence_proxy_async();
@@ -51,6 +54,24 @@ __global__ void __launch_bounds__(384, 1) issue_kernel(int N, int iters, int spi
           ptx::umma_bf16(tmem + (ph << 8), adesc + 4u, bdesc + 4u, idesc, 1u);
           ptx::umma_bf16(tmem + (ph << 8), adesc + 6u, bdesc + 6u, idesc, 1u);
           ptx::umma_commit(commit_bar);
+        }
+        __syncwarp();
+      } else if (mode == 2) {     // the decode kernel's pair loop: two (passing) mbarrier waits, 8 MMAs, three commits
+        ptx::mbar_wait(never_bar, 1);
+        ptx::mbar_wait(commit_bar + 8, 1);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          const uint64_t adesc = desc0 + static_cast<uint64_t>((s * stage_bytes) >> 4);
+          const uint64_t bdesc = adesc + static_cast<uint64_t>(16384u >> 4);
+          ptx::umma_bf16(tmem + (ph << 8), adesc, bdesc, idesc, it > 0 ? 1u : 0u);
+          ptx::umma_bf16(tmem + (ph << 8), adesc + 2u, bdesc + 2u, idesc, 1u);
+          ptx::umma_bf16(tmem + (ph << 8), adesc + 4u, bdesc + 4u, idesc, 1u);
+          ptx::umma_bf16(tmem + (ph << 8), adesc + 6u, bdesc + 6u, idesc, 1u);
+          if ((it & 3) == 3) ptx::umma_commit(commit_bar + 16);
+          if (it & 1) {
+            ptx::umma_commit(commit_bar);
+            ptx::umma_commit(commit_bar + 24);
+          }
         }
         __syncwarp();
       } else {                    // lane 0 only
@@ -95,13 +116,13 @@ int main() {
   const int iters = 20000;
   for (int nblk : {1, 148})
     for (int N : {64, 256})
-      for (int mode : {0, 1})
-        for (int spin : {0, 3, 11}) {
+      for (int mode : {0, 2, 1})
+        for (int spin : {0, 11}) {
           issue_kernel<<<nblk, 384, 227 * 1024 - 1024>>>(N, iters, spin, mode, dc);
           cudaError_t e = cudaDeviceSynchronize();
           long long c = 0;
           cudaMemcpy(&c, dc, 8, cudaMemcpyDeviceToHost);
-          printf("%3d CTAs N=%3d %s spinning warps %2d: %.1f cycles per tcgen05.mma (%s)\n", nblk, N, mode == 0 ? "elect " : "lane0 ", spin,
+          printf("%3d CTAs N=%3d %s spinning warps %2d: %.1f cycles per tcgen05.mma (%s)\n", nblk, N, mode == 0 ? "elect " : mode == 2 ? "decode" : "lane0 ", spin,
                  double(c) / (iters * 4.0), cudaGetErrorString(e));
         }
   (void)smem;
