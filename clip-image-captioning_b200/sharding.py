@@ -55,7 +55,11 @@ def gather_captions(tokens: torch.Tensor, lengths: torch.Tensor, n_items: int, g
 
 def caption_images_sharded(engine, images: torch.Tensor, params, n_items: Optional[int] = None, group=None):
     """`images` holds this rank's shard (see shard_range); returns (tokens, lengths) of ALL images on every rank."""
-    tokens, lengths, _ = engine.caption_images(images, params)
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
     if n_items is None:
-        n_items = images.shape[0] * (dist.get_world_size(group) if dist.is_initialized() else 1)
+        n_items = images.shape[0] * world
+    lo, _ = shard_range(n_items, rank, world)
+    # micro-batches sized for the fastest decode path (Engine.micro_batch_for); Philox streams keyed by global image id
+    tokens, lengths, _ = engine.caption_dataset(images, params, first_row_id=lo)
     return gather_captions(tokens, lengths, n_items, group)

@@ -105,3 +105,22 @@ def test_sampling_is_keyed_by_global_image_id(xl):
     c, _, _ = eng.caption_images(images[:8], p2)
     torch.cuda.synchronize()
     assert (c.cpu() != a).any()
+
+
+def test_caption_dataset_micro_batches(xl):
+    """Engine.caption_dataset: beam search runs 256 // beam images per call (the persistent decode kernel's row limit) and
+    the concatenated result equals the per-chunk calls; sampling is keyed by global image id across micro-batches."""
+    eng, cfg, images = xl
+    pb = eng.gen_params("beam", 6, stop_token=-1, max_stops=0, beam_size=5)
+    assert eng.micro_batch_for(pb) == min(cfg.max_images, 51)
+    tok, ln, sc = eng.caption_dataset(images, pb, micro_batch=7)
+    torch.cuda.synchronize()
+    assert tok.shape == (16, 5, 6) and sc.shape == (16, 5)
+    ref = [eng.caption_images(images[lo:lo + 7], pb) for lo in (0, 7, 14)]
+    torch.cuda.synchronize()
+    assert torch.equal(tok.cpu(), torch.cat([r[0] for r in ref]).cpu())
+    ps = eng.gen_params("sample", 6, stop_token=-1, max_stops=0, top_p=0.9, seed=5)
+    a, _, _ = eng.caption_dataset(images, ps, micro_batch=16, first_row_id=100)
+    b, _, _ = eng.caption_dataset(images, ps, micro_batch=4, first_row_id=100)
+    torch.cuda.synchronize()
+    assert ((a == b).all(dim=1)).float().mean().item() >= 0.8
