@@ -42,7 +42,7 @@ def vit_forward(sd: SD, images: torch.Tensor, heads: int, patch: int, all_tokens
     x = F.conv2d(images.float(), sd["conv1.weight"], stride=patch)            # [B, w, g, g]
     B, w = x.shape[0], x.shape[1]
     x = x.reshape(B, w, -1).permute(0, 2, 1)                                   # [B, g*g, w]
-    cls = sd["class_embedding"].to(x.dtype) + torch.zeros(B, 1, w, dtype=x.dtype)
+    cls = sd["class_embedding"].to(x.dtype) + torch.zeros(B, 1, w, dtype=x.dtype, device=x.device)
     x = torch.cat([cls, x], dim=1) + sd["positional_embedding"]
     x = F.layer_norm(x, (w,), sd["ln_pre.weight"], sd["ln_pre.bias"], 1e-5)
     hd = w // heads

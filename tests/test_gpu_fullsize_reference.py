@@ -1,0 +1,92 @@
+"""Parity at BASELINE.json's FULL sizes (config 2: ViT-B/32 + 8-layer mapper (d = 1600, S = 80) + GPT2-XL) against fp32
+references evaluated on the GPU box itself:
+
+  * the language model against `transformers.GPT2LMHeadModel` -- the very class lms/GPT2.py:6 instantiates and
+    lms/GPT2.py:17-19 calls -- in fp32 on the same bf16-rounded weights: logits within the north-star tolerance
+    (max |delta| <= 2e-2 max |ref|) and greedy tokens compared position by position on the reference's own histories;
+  * ViT features and prefix embeddings against the fp32 oracle restatement (oracle/clipcap_oracle.py, pinned to the
+    reference modules by tests/test_oracle_golden.py) run on CUDA tensors.
+
+Random-init weights give top-1 margins that can be below the bf16 noise of the activations, so token
+agreement is counted per position with teacher forcing (a flip cannot cascade) and every disagreement must be a near-tie
+in the reference logits.
+"""
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import clipcap_oracle as orc  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-2
+
+
+@pytest.fixture(scope="module")
+def full():
+    import clipcap_b200 as cc
+    from clipcap_b200 import synthetic
+    cfg = cc.EngineConfig(max_images=32, max_beam=1, max_ctx=80)
+    eng = cc.Engine(cfg)
+    sds = synthetic.load_synthetic(eng)          # fp32 tensors holding bf16-rounded values, on the device
+    images = synthetic.synthetic_images(32, cfg, device="cuda")
+    yield eng, cfg, sds, images
+    eng.close()
+
+
+def rel(a, b):
+    return (a.float() - b.float()).abs().max().item() / max(b.float().abs().max().item(), 1e-9)
+
+
+def test_vit_and_mapper_match_the_fp32_oracle_at_full_size(full):
+    eng, cfg, sds, images = full
+    feat = eng.vit_encode(images[:8])
+    ref_feat = orc.vit_forward(sds["vit"], images[:8], cfg.vit_heads, cfg.vit_patch)
+    assert rel(feat, ref_feat) <= TOL
+    prefix = eng.map_prefix(ref_feat)            # same input for both sides: isolates the mapper
+    ref_prefix = orc.mapper_forward(sds["mapper"], ref_feat, cfg.map_clip_len, cfg.map_heads, "relu")
+    assert prefix.shape == ref_prefix.shape == (8, cfg.map_prefix_len, cfg.lm_d)
+    assert rel(prefix, ref_prefix) <= TOL
+
+
+def test_gpt2_xl_against_transformers_fp32(full):
+    transformers = pytest.importorskip("transformers")
+    eng, cfg, sds, images = full
+    hf_cfg = transformers.GPT2Config(vocab_size=cfg.lm_vocab, n_positions=cfg.lm_n_pos, n_embd=cfg.lm_d, n_layer=cfg.lm_layers,
+                                     n_head=cfg.lm_heads)
+    with torch.device("cuda"):
+        hf = transformers.GPT2LMHeadModel(hf_cfg)            # what lms/GPT2.py:6 builds
+    missing = hf.load_state_dict(sds["lm"], strict=False)
+    assert all(k.endswith(("attn.bias", "attn.masked_bias", "lm_head.weight")) for k in missing.missing_keys), missing
+    assert not missing.unexpected_keys
+    hf.tie_weights()
+    hf = hf.float().eval()
+
+    N, T = 32, 16
+    prefix = eng.map_prefix(eng.vit_encode(images[:N]))       # [32, 40, 1600]
+    p = eng.gen_params("greedy", T, stop_token=-1, max_stops=0)
+    tokens, _, _ = eng.generate(prefix, p)
+    torch.cuda.synchronize()
+    tokens = tokens.long()
+    emb = torch.cat([prefix, eng.embed_tokens(tokens[:, :T - 1])], dim=1)       # [32, 55, 1600]
+    with torch.no_grad():
+        ref_logits = hf(inputs_embeds=emb).logits.float()                       # lms/GPT2.py:17-19
+    # (a6) teacher-forced logits of the CUDA path over the same embeddings
+    ours = eng.lm_forward(emb)
+    assert rel(ours, ref_logits) <= TOL
+    # greedy tokens of the KV-cached decode against the reference's argmax on the same history
+    P = prefix.shape[1]
+    pred = ref_logits[:, P - 1:P - 1 + T]
+    agree = pred.argmax(-1) == tokens
+    frac = agree.float().mean().item()
+    scale = (pred.max() - pred.min()).item()
+    bad = (~agree).nonzero()
+    for r, t in bad.tolist():
+        margin = (pred[r, t].max() - pred[r, t, tokens[r, t]]).item()
+        assert margin <= TOL * scale, (r, t, margin, scale)   # only near-ties may differ
+    assert frac >= 0.97, frac
+    print("greedy tokens identical to transformers fp32 at %.2f %% of %d positions" % (100 * frac, agree.numel()))
