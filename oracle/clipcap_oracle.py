@@ -110,8 +110,8 @@ def _causal_attention(q, k, v, key_mask=None, q_offset=0):
     hd = q.shape[-1]
     att = (q @ k.transpose(-1, -2)) / math.sqrt(hd)
     Sq, Sk = q.shape[2], k.shape[2]
-    pos_q = torch.arange(Sq).unsqueeze(1) + q_offset
-    allowed = torch.arange(Sk).unsqueeze(0) <= pos_q
+    pos_q = torch.arange(Sq, device=q.device).unsqueeze(1) + q_offset
+    allowed = torch.arange(Sk, device=q.device).unsqueeze(0) <= pos_q
     att = att.masked_fill(~allowed, float("-inf"))
     if key_mask is not None:
         att = att.masked_fill(~key_mask.bool()[:, None, None, :], float("-inf"))
@@ -160,7 +160,7 @@ def _rotate_every_two(x):  # HF modeling_gptj.py rotate_every_two
 
 def _gptj_rotary(x, positions, rotary_dim):
     """x [B,S,H,hd]; HF create_sinusoidal_positions + apply_rotary_pos_emb on the first rotary_dim dims."""
-    inv_freq = 1.0 / (10000 ** (torch.arange(0, rotary_dim, 2, dtype=torch.int64).float() / rotary_dim))
+    inv_freq = 1.0 / (10000 ** (torch.arange(0, rotary_dim, 2, dtype=torch.int64, device=x.device).float() / rotary_dim))
     ang = positions.float()[:, None] * inv_freq[None, :]
     sin = torch.repeat_interleave(torch.sin(ang), 2, dim=-1)[None, :, None, :]
     cos = torch.repeat_interleave(torch.cos(ang), 2, dim=-1)[None, :, None, :]
@@ -178,7 +178,7 @@ def gptj_forward(sd: SD, embeds: torch.Tensor, heads: int, rotary_dim: int,
     hd = d // heads
     n_layers = 1 + max(int(k.split(".")[2]) for k in sd if k.startswith("transformer.h."))
     off = past[0][0].shape[2] if past else 0
-    pos = torch.arange(off, off + S)
+    pos = torch.arange(off, off + S, device=embeds.device)
     h = embeds.float()
     present = []
     for l in range(n_layers):
@@ -341,8 +341,8 @@ def generate_beam(lm: OracleLM, embeds: torch.Tensor, beam_size: int = 5, entry_
     use_cache=False re-runs the full forward every step exactly like the reference."""
     tokens = None
     scores = None
-    seq_lengths = torch.ones(beam_size)
-    has_stopped = torch.zeros(beam_size, dtype=torch.bool)
+    seq_lengths = torch.ones(beam_size, device=embeds.device)
+    has_stopped = torch.zeros(beam_size, dtype=torch.bool, device=embeds.device)
     past = None
     step_in = embeds
     for _ in range(entry_length):
@@ -434,9 +434,9 @@ def generate_greedy(lm: OracleLM, embeds: torch.Tensor, entry_length: int, stop_
     per-row application of the batch-1 rules).  Returns tokens [B, entry_length] (rows keep decoding after their
     stop token; only the first `lengths[b]` ids are the caption) and lengths [B]."""
     B = embeds.shape[0]
-    tokens = torch.zeros(B, entry_length, dtype=torch.int64)
-    lengths = torch.zeros(B, dtype=torch.int64)
-    done = torch.zeros(B, dtype=torch.bool)
+    tokens = torch.zeros(B, entry_length, dtype=torch.int64, device=embeds.device)
+    lengths = torch.zeros(B, dtype=torch.int64, device=embeds.device)
+    done = torch.zeros(B, dtype=torch.bool, device=embeds.device)
     past, step_in = None, embeds
     for t in range(entry_length):
         if use_cache:

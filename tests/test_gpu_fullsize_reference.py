@@ -90,3 +90,39 @@ def test_gpt2_xl_against_transformers_fp32(full):
         assert margin <= TOL * scale, (r, t, margin, scale)   # only near-ties may differ
     assert frac >= 0.97, frac
     print("greedy tokens identical to transformers fp32 at %.2f %% of %d positions" % (100 * frac, agree.numel()))
+
+
+def test_beam_search_against_the_reference_loop_at_full_size(full):
+    """generate_beam (inference.py:70-148, restated in the oracle: batch-1 loop in fp32 on the GPU, with the oracle's own
+    KV cache -- numerically the same forward, pinned in tests/test_oracle_golden.py) for GPT2-XL, beam 5, one image at a
+    time, against the on-device beam search over a batch of images."""
+    eng_small, cfg, sds, images = full
+    import clipcap_b200 as cc
+    cfg_b = cc.EngineConfig(max_images=8, max_beam=5, max_ctx=80)
+    eng = cc.Engine(cfg_b)
+    for k, pre in (("lm", "language_model."), ("mapper", "clip_project."), ("vit", "visual.")):
+        eng.load_state_dict(sds[k], prefix=pre)
+    eng.check_weights()
+    N, T = 6, 8
+    prefix = eng.map_prefix(eng.vit_encode(images[:N]))
+    p = eng.gen_params("beam", T, stop_token=-1, max_stops=0, beam_size=5)
+    tok, ln, sc = eng.generate(prefix, p)
+    torch.cuda.synchronize()
+    tok, sc = tok.cpu(), sc.cpu()
+    lm = orc.OracleLM(sds["lm"], "gpt2", cfg.lm_heads)
+    same_best, same_set = 0, 0
+    for i in range(N):
+        with torch.no_grad():
+            rt, rl, rs, order = orc.generate_beam(lm, prefix[i:i + 1].float(), beam_size=5, entry_length=T, stop_token=-1,
+                                                  use_cache=True)
+        rt, rs, order = rt.cpu(), rs.cpu(), order.cpu()
+        best_ref = rt[order[0]].tolist()
+        best = tok[i, int(sc[i].argmax())].tolist()
+        same_best += best == best_ref
+        same_set += sorted(map(tuple, tok[i].tolist())) == sorted(map(tuple, rt.tolist()))
+        if best == best_ref:
+            assert abs(float(sc[i].max()) - float(rs[order[0]])) <= 2e-2 * max(1.0, abs(float(rs[order[0]])))
+    eng.close()
+    print("beam 5, GPT2-XL: best caption identical for %d / %d images, all five beams for %d / %d" % (same_best, N, same_set, N))
+    # random-init log-probabilities are nearly flat, so losing beams swap on near-ties; the winner must hold
+    assert same_best >= N - 1
