@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libclipcap_b200.so")
 
 DTYPE_F32, DTYPE_F16, DTYPE_BF16 = 0, 1, 2
 LM_GPT2, LM_GPTJ = 0, 1
-MAP_NONE, MAP_TRANSFORMER, MAP_MLP = 0, 1, 2
+MAP_NONE, MAP_TRANSFORMER, MAP_MLP, MAP_TRANSFORMER_ALL = 0, 1, 2, 3
 ACT = {"none": 0, "relu": 1, "quick_gelu": 2, "gelu_new": 3, "gelu": 4, "elu": 5, "selu": 6, "tanh": 7}
 GEN_GREEDY, GEN_SAMPLE, GEN_BEAM = 0, 1, 2
 
@@ -46,6 +46,7 @@ PROTOTYPES = {
     "ccb_load_weight": (_I, [_P, C.c_char_p, _P, _I, C.POINTER(_L), _I, _P]),
     "ccb_weights_complete": (_I, [_P]),
     "ccb_vit_encode": (_I, [_P, _P, _I, _I, _P, _P]),
+    "ccb_vit_encode_tokens": (_I, [_P, _P, _I, _I, _P, _P]),
     "ccb_map_prefix": (_I, [_P, _P, _I, _P, _P]),
     "ccb_embed_tokens": (_I, [_P, _P, _I, _P, _P]),
     "ccb_lm_forward": (_I, [_P, _P, _I, _I, _P, _P, _L, _I, _P]),

@@ -244,7 +244,7 @@ int block_forward(ccb_ctx* c, const Block& b, int M, const BlockShape& sh, AttnF
   return 0;
 }
 
-int vit_forward(ccb_ctx* c, const void* images, int dtype, int B, float* feat_out, cudaStream_t s) {
+int vit_forward(ccb_ctx* c, const void* images, int dtype, int B, float* feat_out, cudaStream_t s, bool all_tokens = false) {
   const ccb_model_desc& D = c->desc;
   if (!D.vit_present) return fail(c, "context was created without an image encoder");
   if (B <= 0 || B > D.max_images) return fail(c, "vit_encode: B=%d outside [1, max_images=%d]", B, D.max_images);
@@ -262,6 +262,12 @@ int vit_forward(ccb_ctx* c, const void* images, int dtype, int B, float* feat_ou
     };
     if (block_forward(c, c->vit[l], M, sh, attn, s)) return -1;
   }
+  if (all_tokens) {
+    // the fork's patched forward (inference.py:421-444): no ln_post, no CLS extraction: x @ proj for every token
+    RUN(cast_f32_bf16(c->h, w, c->x, w, M, w, s));
+    RUN(linear(c, c->x, w, M, c->vit_proj, CCB_ACT_NONE, nullptr, 0, feat_out, D.vit_out, 0, s));
+    return 0;
+  }
   // ln_post(x[:, 0, :]) @ proj
   RUN(layernorm_f32_bf16(c->h, static_cast<long long>(S) * w, c->vit_ln_post.g, c->vit_ln_post.b, 1e-5f, c->x, w, B, w, s));
   RUN(linear(c, c->x, w, B, c->vit_proj, CCB_ACT_NONE, nullptr, 0, feat_out, D.vit_out, 0, s));
@@ -274,7 +280,7 @@ int map_forward(ccb_ctx* c, const float* feat, int B, float* out, int out_rows_p
   if (D.map_kind == CCB_MAP_NONE) return fail(c, "context was created without a prefix mapper");
   if (B <= 0 || B > D.max_images) return fail(c, "map_prefix: B=%d outside [1, max_images=%d]", B, D.max_images);
   const int d = D.lm_d, P = D.map_prefix_len, dc = D.map_dim_clip;
-  RUN(cast_f32_bf16(feat, dc, c->feat_bf16, dc, B, dc, s));
+  if (D.map_kind != CCB_MAP_TRANSFORMER_ALL) RUN(cast_f32_bf16(feat, dc, c->feat_bf16, dc, B, dc, s));
   if (D.map_kind == CCB_MAP_MLP) {
     // upstream ClipCap MLP mapper: Linear(dc, d*P/2) -> Tanh -> Linear(d*P/2, d*P), viewed as [B, P, d]
     RUN(linear(c, c->feat_bf16, dc, B, c->map_linear, CCB_ACT_TANH, nullptr, 0, c->mlp, D.map_hidden, 1, s));
@@ -283,10 +289,37 @@ int map_forward(ccb_ctx* c, const float* feat, int B, float* out, int out_rows_p
     return 0;
   }
   const int CL = D.map_clip_len, S = CL + P, M = B * S;
+  if (D.map_kind == CCB_MAP_TRANSFORMER_ALL) {
+    // TransformerMapperAllFeatures.forward (layers/Transformer.py:186-203): feat [B, CL, dc]; x = linear(feat) (+
+    // pos_embeddings) per visual token in rows [0, CL) of every sequence, prefix_const in rows [CL, S).  The rows are
+    // pre-filled with pos_embeddings (or zeros) and the GEMM adds its result in place (row remap CL -> S).
+    RUN(cast_f32_bf16(feat, dc, c->feat_bf16, dc, B * CL, dc, s));
+    RUN(mapper_fill_const(c->map_prefix_const, c->h, B, CL, P, d, s));
+    RUN(mapper_fill_pos(c->map_pos_present ? c->map_pos : nullptr, c->h, B, CL, P, d, s));
+    GemmArgs g;
+    g.act = c->feat_bf16;
+    g.lda = dc;
+    g.tokens = B * CL;
+    g.weight = c->map_linear.w;
+    g.features = d;
+    g.K = dc;
+    g.bias = c->map_linear.bias;
+    g.residual = c->h;
+    g.ldr = d;
+    g.out = c->h;
+    g.ldo = d;
+    g.rg_in = CL;
+    g.rg_out = S;
+    g.rg_off = 0;
+    g.force_orientation = 1;   // the row remap lives in the token-major kernels
+    g.allow_pdl = 1;
+    RUN(gemm_launch(g, c->gemm_ws, s));
+  } else {
   // linear(x).view(B, clip_len, d) lands in rows [0, clip_len) of every sequence (row pitch S*d);
   // rows [clip_len, S) are the learned prefix_const (layers/Transformer.py:154-157)
   RUN(linear(c, c->feat_bf16, dc, B, c->map_linear, CCB_ACT_NONE, nullptr, 0, c->h, static_cast<long long>(S) * d, 0, s));
   RUN(mapper_fill_const(c->map_prefix_const, c->h, B, CL, P, d, s));
+  }
   BlockShape sh{d, D.map_hidden, act_code(D.map_act), 1e-5f, false};
   const int H = D.map_heads, hd = d / H;
   const float scale = 1.0f / sqrtf(static_cast<float>(hd));
@@ -641,7 +674,7 @@ int ccb_create(ccb_ctx** out, const ccb_model_desc* desc, int device) {
   if (D.lm_arch != CCB_LM_GPT2 && D.lm_arch != CCB_LM_GPTJ) return fail(nullptr, "ccb_create: unknown lm_arch");
   if (D.max_images <= 0 || D.max_beam <= 0 || D.max_ctx <= 0 || D.max_lm_tokens <= 0 || D.page_tokens <= 0)
     return fail(nullptr, "ccb_create: capacities must be positive");
-  if (D.map_kind == CCB_MAP_TRANSFORMER && (D.map_heads <= 0 || D.lm_d % D.map_heads || (D.lm_d / D.map_heads) % 2 ||
+  if ((D.map_kind == CCB_MAP_TRANSFORMER || D.map_kind == CCB_MAP_TRANSFORMER_ALL) && (D.map_heads <= 0 || D.lm_d % D.map_heads || (D.lm_d / D.map_heads) % 2 ||
                                             D.map_hidden % 64 || D.map_dim_clip % 64))
     return fail(nullptr, "ccb_create: bad mapper dimensions");
   if (D.map_kind == CCB_MAP_MLP && (D.map_hidden % 64 || D.map_dim_clip % 64)) return fail(nullptr, "ccb_create: bad MLP mapper dimensions");
@@ -711,9 +744,16 @@ int ccb_create(ccb_ctx** out, const ccb_model_desc* desc, int device) {
 
   // ---- mapper
   int map_S = 0;
-  if (D.map_kind == CCB_MAP_TRANSFORMER) {
+  if (D.map_kind == CCB_MAP_TRANSFORMER || D.map_kind == CCB_MAP_TRANSFORMER_ALL) {
     map_S = D.map_clip_len + D.map_prefix_len;
-    make_linear(c, a, c->map_linear, D.map_clip_len * d, D.map_dim_clip, true);
+    if (D.map_kind == CCB_MAP_TRANSFORMER_ALL) {
+      make_linear(c, a, c->map_linear, d, D.map_dim_clip, true);
+      c->map_pos = a.arr<float>(static_cast<size_t>(D.map_clip_len) * d);
+      add_slot(c, "clip_project.pos_embeddings", WeightSlot::VECTOR_F32, c->map_pos, static_cast<long long>(D.map_clip_len) * d,
+               1, 1, &c->map_pos_present, true);   // optional (use_pos_embeddings, layers/Transformer.py:181-185)
+    } else {
+      make_linear(c, a, c->map_linear, D.map_clip_len * d, D.map_dim_clip, true);
+    }
     slot_linear(c, "clip_project.linear", c->map_linear);
     c->map_prefix_const = a.arr<float>(static_cast<size_t>(D.map_prefix_len) * d);
     add_slot(c, "clip_project.prefix_const", WeightSlot::VECTOR_F32, c->map_prefix_const,
@@ -804,8 +844,9 @@ int ccb_create(ccb_ctx** out, const ccb_model_desc* desc, int device) {
     c->patch_emb = a.arr<float>(static_cast<size_t>(D.max_images) * np * D.vit_width);
   }
   const int dc = std::max(D.map_dim_clip, D.vit_present ? D.vit_out : 0);
-  c->feat = a.arr<float>(static_cast<size_t>(D.max_images) * std::max(dc, 1));
-  c->feat_bf16 = a.arr<bf16>(static_cast<size_t>(D.max_images) * std::max(dc, 1));
+  const int feat_tokens = D.map_kind == CCB_MAP_TRANSFORMER_ALL ? std::max(D.map_clip_len, vit_S) : 1;   // per image
+  c->feat = a.arr<float>(static_cast<size_t>(D.max_images) * feat_tokens * std::max(dc, 1));
+  c->feat_bf16 = a.arr<bf16>(static_cast<size_t>(D.max_images) * feat_tokens * std::max(dc, 1));
   c->prefix = a.arr<float>(static_cast<size_t>(D.max_images) * (std::max(D.map_prefix_len, 0) + 1) * d);
   c->ldv = (static_cast<int64_t>(V) + 63) / 64 * 64;
   c->logits = a.arr<float>(static_cast<size_t>(std::max(c->max_rows, D.max_images)) * c->ldv);
@@ -954,6 +995,11 @@ int ccb_vit_encode(ccb_ctx* c, const void* images, int dtype, int B, float* feat
   return vit_forward(c, images, dtype, B, feat_out, static_cast<cudaStream_t>(stream));
 }
 
+int ccb_vit_encode_tokens(ccb_ctx* c, const void* images, int dtype, int B, float* tokens_out, void* stream) {
+  if (!c || !images || !tokens_out) return fail(c, "ccb_vit_encode_tokens: null argument");
+  return vit_forward(c, images, dtype, B, tokens_out, static_cast<cudaStream_t>(stream), true);
+}
+
 int ccb_map_prefix(ccb_ctx* c, const float* feat, int B, float* prefix_out, void* stream) {
   if (!c || !feat || !prefix_out) return fail(c, "ccb_map_prefix: null argument");
   return map_forward(c, feat, B, prefix_out, c->desc.map_prefix_len, static_cast<cudaStream_t>(stream));
@@ -996,7 +1042,10 @@ int ccb_caption_images(ccb_ctx* c, const ccb_gen_params* p, const void* images, 
   cudaStream_t s = c->work;
   const int P = c->desc.map_prefix_len, d = c->desc.lm_d;
   const int extra = append_bos >= 0 ? 1 : 0;
-  int r = vit_forward(c, images, dtype, N, c->feat, s);
+  const bool all_tokens = c->desc.map_kind == CCB_MAP_TRANSFORMER_ALL;
+  if (all_tokens && c->desc.vit_present && c->desc.map_clip_len != (c->desc.vit_image / c->desc.vit_patch) * (c->desc.vit_image / c->desc.vit_patch) + 1)
+    return fail(c, "ccb_caption_images: map_clip_len=%d does not match the ViT's token count", c->desc.map_clip_len);
+  int r = vit_forward(c, images, dtype, N, c->feat, s, all_tokens);
   if (r == 0) r = map_forward(c, c->feat, N, c->prefix, P + extra, s);
   if (r == 0 && extra) {
     if (append_bos >= c->desc.lm_vocab) {

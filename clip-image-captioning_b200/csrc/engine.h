@@ -70,6 +70,8 @@ struct ccb_ctx {
   // mapper
   ccb::Linear map_linear;         // transformer mapper: [clip_len*d, dim_clip]; MLP mapper: first layer
   ccb::Linear map_mlp2;           // MLP mapper second layer
+  float* map_pos = nullptr;          // TransformerMapperAllFeatures.pos_embeddings [clip_len, d] (optional)
+  bool map_pos_present = false;
   float* map_prefix_const = nullptr;  // [P, d]
   std::vector<ccb::Block> mapper;
   // ViT

@@ -89,6 +89,8 @@ int vit_assemble_lnpre(const float* patch_emb, const float* cls, const float* po
 // mapper: seq[b, clip_len + p, :] = prefix_const[p, :]  (f32 stream [B, S, d]); rows [0, clip_len) are written
 // by the `linear` GEMM epilogue.
 int mapper_fill_const(const float* prefix_const, float* seq, int B, int clip_len, int P, int d, cudaStream_t s);
+// all-features mapper: seq[b, t, :] = pos[t, :] (zeros when pos == null) for t < clip_len
+int mapper_fill_pos(const float* pos, float* seq, int B, int clip_len, int P, int d, cudaStream_t s);
 // f32 -> bf16 cast of a [rows, d] block (leading dims in elements)
 int cast_f32_bf16(const float* x, long long ldx, bf16* y, long long ldy, int rows, int d, cudaStream_t s);
 // bf16/f32 embedding gather: h[r, :] = table[tok[r], :] (+ wpe[pos[r], :] if wpe) -> f32 [rows, d]

@@ -224,6 +224,15 @@ __global__ void __launch_bounds__(256) mapper_fill_const_kernel(const float* __r
   for (int c = threadIdx.x; c < d / 4; c += blockDim.x) dst[c] = __ldg(src + c);
 }
 
+__global__ void __launch_bounds__(256) mapper_fill_pos_kernel(const float* __restrict__ pos, float* __restrict__ seq,
+                                                              int clip_len, int P, int d) {
+  // grid: (clip_len, B)
+  const int t = blockIdx.x, b = blockIdx.y;
+  float4* dst = reinterpret_cast<float4*>(seq + (static_cast<long long>(b) * (clip_len + P) + t) * d);
+  const float4* src = pos ? reinterpret_cast<const float4*>(pos + static_cast<long long>(t) * d) : nullptr;
+  for (int c = threadIdx.x; c < d / 4; c += blockDim.x) dst[c] = src ? __ldg(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
 __global__ void __launch_bounds__(256) cast_kernel(const float* __restrict__ x, long long ldx, bf16* __restrict__ y,
                                                    long long ldy, int d) {
   const float* xr = x + static_cast<long long>(blockIdx.x) * ldx;
@@ -397,6 +406,14 @@ int mapper_fill_const(const float* prefix_const, float* seq, int B, int clip_len
   if (B <= 0 || P <= 0) return 0;
   if (d % 4) return (int)cudaErrorInvalidValue;
   mapper_fill_const_kernel<<<dim3(P, B), 256, 0, s>>>(prefix_const, seq, clip_len, P, d);
+  CCB_LAUNCH_CHECK();
+  return 0;
+}
+
+int mapper_fill_pos(const float* pos, float* seq, int B, int clip_len, int P, int d, cudaStream_t s) {
+  if (B <= 0 || clip_len <= 0) return 0;
+  if (d % 4) return (int)cudaErrorInvalidValue;
+  mapper_fill_pos_kernel<<<dim3(clip_len, B), 256, 0, s>>>(pos, seq, clip_len, P, d);
   CCB_LAUNCH_CHECK();
   return 0;
 }

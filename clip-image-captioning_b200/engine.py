@@ -29,7 +29,8 @@ class EngineConfig:
     lm_n_pos: int = 1024
     lm_rotary_dim: int = 0
     lm_ln_eps: float = 1e-5
-    map_kind: str = "transformer"    # "transformer" | "mlp" | "none"
+    map_kind: str = "transformer"    # "transformer" | "transformer_all" (use_all_vit_features: one mapper token per ViT
+                                     # token, map_clip_len = ViT tokens, layers/Transformer.py:164-203) | "mlp" | "none"
     map_dim_clip: int = 512          # hparams.prefix_size
     map_clip_len: int = 40           # hparams.clip_prefix_length
     map_prefix_len: int = 40         # hparams.prefix_length
@@ -56,7 +57,8 @@ class EngineConfig:
         d.lm_arch = {"gpt2": _lib.LM_GPT2, "gptj": _lib.LM_GPTJ}[self.lm_arch]
         d.lm_d, d.lm_layers, d.lm_heads, d.lm_vocab = self.lm_d, self.lm_layers, self.lm_heads, self.lm_vocab
         d.lm_n_pos, d.lm_rotary_dim, d.lm_ln_eps = self.lm_n_pos, self.lm_rotary_dim, self.lm_ln_eps
-        d.map_kind = {"none": _lib.MAP_NONE, "transformer": _lib.MAP_TRANSFORMER, "mlp": _lib.MAP_MLP}[self.map_kind]
+        d.map_kind = {"none": _lib.MAP_NONE, "transformer": _lib.MAP_TRANSFORMER, "mlp": _lib.MAP_MLP,
+                      "transformer_all": _lib.MAP_TRANSFORMER_ALL}[self.map_kind]
         d.map_dim_clip, d.map_clip_len, d.map_prefix_len = self.map_dim_clip, self.map_clip_len, self.map_prefix_len
         d.map_heads, d.map_layers = self.map_heads, self.map_layers
         hidden = self.map_hidden
@@ -175,11 +177,20 @@ class Engine:
         self._check(self.lib.ccb_weights_complete(self._h))
 
     # ------------------------------------------------------------------------------------------ stages
-    def vit_encode(self, images: torch.Tensor) -> torch.Tensor:
+    def vit_encode(self, images: torch.Tensor, all_tokens: Optional[bool] = None) -> torch.Tensor:
+        """[B, vit_out] (CLS token through ln_post and proj), or with all_tokens (default for the "transformer_all"
+        mapper: the fork's patched forward, inference.py:421-444) [B, 1 + patches, vit_out]."""
         images = self._dev(images)
         if images.dtype not in _TORCH_DTYPE:
             images = images.float()
         B = images.shape[0]
+        if all_tokens is None:
+            all_tokens = self.cfg.map_kind == "transformer_all"
+        if all_tokens:
+            n = (self.cfg.vit_image // self.cfg.vit_patch) ** 2 + 1
+            out = torch.empty(B, n, self.cfg.vit_out, device=self.device, dtype=torch.float32)
+            self._check(self.lib.ccb_vit_encode_tokens(self._h, _ptr(images), _TORCH_DTYPE[images.dtype], B, _ptr(out), self._stream()))
+            return out
         out = torch.empty(B, self.cfg.vit_out, device=self.device, dtype=torch.float32)
         self._check(self.lib.ccb_vit_encode(self._h, _ptr(images), _TORCH_DTYPE[images.dtype], B, _ptr(out), self._stream()))
         return out
@@ -187,6 +198,11 @@ class Engine:
     def map_prefix(self, feat: torch.Tensor) -> torch.Tensor:
         feat = self._dev(feat, torch.float32)
         B = feat.shape[0]
+        if self.cfg.map_kind == "transformer_all":
+            if feat.dim() != 3 or feat.shape[1] != self.cfg.map_clip_len or feat.shape[2] != self.cfg.map_dim_clip:
+                raise ValueError("transformer_all mapper expects features [B, %d, %d]" % (self.cfg.map_clip_len, self.cfg.map_dim_clip))
+        elif feat.dim() != 2 or feat.shape[1] != self.cfg.map_dim_clip:
+            raise ValueError("mapper expects features [B, %d]" % self.cfg.map_dim_clip)
         out = torch.empty(B, self.cfg.map_prefix_len, self.cfg.lm_d, device=self.device, dtype=torch.float32)
         self._check(self.lib.ccb_map_prefix(self._h, _ptr(feat), B, _ptr(out), self._stream()))
         return out

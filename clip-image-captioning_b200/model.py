@@ -10,7 +10,8 @@ from .lms import GPT2, GPTJ
 
 
 class _ClipProject:
-    """`model.clip_project(prefix)` -> [B, P, d] (layers/Transformer.py:153-161)."""
+    """`model.clip_project(prefix)` -> [B, P, d] (layers/Transformer.py:153-161; with use_all_vit_features the
+    TransformerMapperAllFeatures of layers/Transformer.py:164-203 over [B, tokens, 512] features)."""
 
     def __init__(self, engine: Engine):
         self.engine = engine
@@ -22,7 +23,8 @@ class _ClipProject:
 
 
 class _VisualEncoder:
-    """`clip_model.encode_image(img)` / `model.visual_encoder(img)` -> [B, 512] f32 (inference.py:311)."""
+    """`clip_model.encode_image(img)` / `model.visual_encoder(img)` -> [B, 512] f32 (inference.py:311), or, when the
+    model was built with use_all_vit_features (inference.py:421-444), every projected token [B, 50, 512]."""
 
     def __init__(self, engine: Engine):
         self.engine = engine

@@ -75,7 +75,11 @@ def mapper_state_dict(cfg: EngineConfig, seed: int = 1235, device="cpu", prefix_
         _linear(sd, "model.2", d * cfg.map_prefix_len, hidden, g, device)
         return sd
     hidden = cfg.map_hidden or int(d * cfg.map_mlp_ratio)
-    _linear(sd, "linear", cfg.map_clip_len * d, cfg.map_dim_clip, g, device)
+    if cfg.map_kind == "transformer_all":     # layers/Transformer.py:178-185
+        _linear(sd, "linear", d, cfg.map_dim_clip, g, device)
+        sd["pos_embeddings"] = _rn(g, (cfg.map_clip_len, d), 1.0, device)
+    else:
+        _linear(sd, "linear", cfg.map_clip_len * d, cfg.map_dim_clip, g, device)
     sd["prefix_const"] = _rn(g, (cfg.map_prefix_len, d), prefix_init_std, device)
     for l in range(cfg.map_layers):
         p = "transformer.layers.%d." % l

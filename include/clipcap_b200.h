@@ -33,7 +33,9 @@ typedef struct ccb_ctx ccb_ctx;
 
 enum { CCB_DTYPE_F32 = 0, CCB_DTYPE_F16 = 1, CCB_DTYPE_BF16 = 2 };
 enum { CCB_LM_GPT2 = 0, CCB_LM_GPTJ = 1 };
-enum { CCB_MAP_NONE = 0, CCB_MAP_TRANSFORMER = 1, CCB_MAP_MLP = 2 };
+/* TRANSFORMER_ALL: layers/Transformer.py:164-203 (TransformerMapperAllFeatures: one mapper token per ViT token, the
+ * fork's default training configuration, train.py:73 use_all_vit_features=True) */
+enum { CCB_MAP_NONE = 0, CCB_MAP_TRANSFORMER = 1, CCB_MAP_MLP = 2, CCB_MAP_TRANSFORMER_ALL = 3 };
 /* activation codes (mapper act_fn_name, layers/Transformer.py:117-130; ViT QuickGELU; GPT gelu_new) */
 enum {
   CCB_ACT_NONE = 0, CCB_ACT_RELU = 1, CCB_ACT_QUICKGELU = 2, CCB_ACT_GELU_NEW = 3, CCB_ACT_GELU = 4,
@@ -45,7 +47,8 @@ typedef struct ccb_model_desc {
   /* language model: lms/GPT2.py:6-19 (HF GPT2LMHeadModel) or lms/GPTJ.py:5-18 (HF GPTJForCausalLM) */
   int32_t lm_arch, lm_d, lm_layers, lm_heads, lm_vocab, lm_n_pos, lm_rotary_dim;
   float lm_ln_eps;
-  /* prefix mapper: layers/Transformer.py:133-161 (TransformerMapper); MLP = upstream ClipCap MLP mapper */
+  /* prefix mapper: layers/Transformer.py:133-161 (TransformerMapper); MLP = upstream ClipCap MLP mapper;
+   * TRANSFORMER_ALL: map_clip_len = number of ViT tokens (50 for ViT-B/32 @ 224), optional pos_embeddings */
   int32_t map_kind, map_dim_clip, map_clip_len, map_prefix_len, map_heads, map_layers, map_hidden, map_act;
   /* image encoder: OpenAI CLIP VisionTransformer (call sites inference.py:311, evaluate_model.py:359) */
   int32_t vit_present, vit_image, vit_patch, vit_width, vit_layers, vit_heads, vit_out;
@@ -100,8 +103,12 @@ CCB_API int ccb_weights_complete(ccb_ctx* ctx);
 /* clip_model.encode_image(image) (inference.py:311) / model.visual_encoder(image_tensor)
  * (evaluate_model.py:359): images [B,3,H,W] NCHW -> feat_out [B, vit_out] f32 */
 CCB_API int ccb_vit_encode(ccb_ctx* ctx, const void* images, int dtype, int B, float* feat_out, void* stream);
+/* the patched VisionTransformer.forward of the all-features path (inference.py:421-444, evaluate_model.py: same patch):
+ * no ln_post / CLS extraction, every token projected: images [B,3,H,W] -> tokens_out [B, 1 + (H/patch)^2, vit_out] f32 */
+CCB_API int ccb_vit_encode_tokens(ccb_ctx* ctx, const void* images, int dtype, int B, float* tokens_out, void* stream);
 /* model.clip_project(prefix) (inference.py:312, model.py:137; layers/Transformer.py:153-161):
- * feat [B, map_dim_clip] f32 -> prefix_out [B, map_prefix_len, lm_d] f32 */
+ * feat [B, map_dim_clip] f32 -> prefix_out [B, map_prefix_len, lm_d] f32.  With CCB_MAP_TRANSFORMER_ALL
+ * (layers/Transformer.py:186-203) feat is [B, map_clip_len, map_dim_clip], the output of ccb_vit_encode_tokens. */
 CCB_API int ccb_map_prefix(ccb_ctx* ctx, const float* feat, int B, float* prefix_out, void* stream);
 /* language_model.get_embedding_text(tokens) (lms/GPT2.py:14-15): out [n, lm_d] f32 */
 CCB_API int ccb_embed_tokens(ccb_ctx* ctx, const int32_t* tokens, int n, float* out, void* stream);

@@ -97,6 +97,28 @@ def mapper_forward(sd: SD, feat: torch.Tensor, clip_length: int, heads: int, act
     return x[:, clip_length:]
 
 
+def mapper_all_forward(sd: SD, feats: torch.Tensor, heads: int, act: str = "relu") -> torch.Tensor:
+    """TransformerMapperAllFeatures.forward (layers/Transformer.py:186-203): feats [B, T, dim_clip] (every projected ViT
+    token, inference.py:421-444) -> linear per token (+ pos_embeddings when present) || prefix_const -> transformer ->
+    the prefix rows.  `sd` = TransformerMapperAllFeatures.state_dict()."""
+    B, T = feats.shape[0], feats.shape[1]
+    d = sd["prefix_const"].shape[1]
+    x = F.linear(feats.float(), sd["linear.weight"], sd["linear.bias"])
+    if "pos_embeddings" in sd:
+        x = x + sd["pos_embeddings"].unsqueeze(0)
+    x = torch.cat((x, sd["prefix_const"].unsqueeze(0).expand(B, -1, -1)), dim=1)
+    n_layers = 1 + max(int(k.split(".")[2]) for k in sd if k.startswith("transformer.layers."))
+    fn = ACTS[act]
+    for l in range(n_layers):
+        p = "transformer.layers.%d." % l
+        y = F.layer_norm(x, (d,), sd[p + "norm1.weight"], sd[p + "norm1.bias"], 1e-5)
+        x = x + mapper_attention(sd, p + "attn.", y, heads)
+        y = F.layer_norm(x, (d,), sd[p + "norm2.weight"], sd[p + "norm2.bias"], 1e-5)
+        y = fn(F.linear(y, sd[p + "mlp.fc1.weight"], sd[p + "mlp.fc1.bias"]))
+        x = x + F.linear(y, sd[p + "mlp.fc2.weight"], sd[p + "mlp.fc2.bias"])
+    return x[:, T:]
+
+
 def mlp_mapper_forward(sd: SD, feat: torch.Tensor, prefix_length: int) -> torch.Tensor:
     """Upstream ClipCap MLP mapper (not in this fork; README.md:36 only): Linear -> Tanh -> Linear, viewed
     [B, P, d].  PARITY UNPINNED: no reference code or golden vector exists for it."""

@@ -284,3 +284,46 @@ def test_typical_filtering_matches_reference(tiny_engine):
     assert close_sets(tiny_engine.sample(L, p, return_filtered=True)[1], tx["topp_0.9_typ_0.5"])
     assert torch.equal(S.typical_filtering(L, 0.0, engine=tiny_engine), L)
     assert torch.equal(S.typical_filtering(L, torch.zeros(L.shape[0]), engine=tiny_engine), L)
+
+
+@pytest.mark.parametrize("key", ["pos", "nopos"])
+def test_all_vit_features_path(key):
+    """use_all_vit_features (the fork's default, train.py:73): ccb_vit_encode_tokens + the TransformerMapperAllFeatures
+    mapper + forward logits + beam captions against the fixture generated by the unmodified reference modules."""
+    import clipcap_b200 as cc
+    fx = torch.load(os.path.join(GOLDEN, "tiny_allfeatures.pt"), weights_only=False)
+    cfg = cc.EngineConfig(
+        lm_arch="gpt2", lm_d=fx["d"], lm_layers=2, lm_heads=fx["heads"], lm_vocab=fx["V"], lm_n_pos=64,
+        map_kind="transformer_all", map_dim_clip=fx["dim_clip"], map_clip_len=fx["T"], map_prefix_len=fx["P"],
+        map_heads=fx["map_heads"], map_layers=2, vit_image=fx["vit_image"], vit_patch=fx["vit_patch"],
+        vit_width=fx["vit_width"], vit_layers=fx["vit_layers"], vit_heads=fx["vit_heads"], vit_out=fx["dim_clip"],
+        max_images=8, max_beam=5, max_ctx=32, page_tokens=4)
+    eng = cc.Engine(cfg)
+    eng.load_state_dict(fx["sd_lm"], prefix="language_model.")
+    eng.load_state_dict(fx["sd_mapper_" + key], prefix="clip_project.")
+    eng.load_state_dict(fx["sd_vit"], prefix="visual.")
+    eng.check_weights()
+    toks = eng.vit_encode(fx["images"])
+    assert toks.shape == (3, fx["T"], fx["dim_clip"])
+    assert rel_err(toks, fx["vit_tokens"]) <= TOL
+    prefix = eng.map_prefix(fx["vit_tokens"])
+    assert rel_err(prefix, fx["prefix_" + key]) <= TOL
+    model = cc.CLIPCaptionModel(eng)
+    logits = model(fx["cap_tokens"], fx["vit_tokens"], torch.ones(3, 6, dtype=torch.bool)).logits
+    assert rel_err(logits, fx["forward_logits_" + key]) <= TOL
+    # beam search from the reference's prefix embeddings (the language-model half alone, like the other beam tests) ...
+    p = eng.gen_params("beam", 10, stop_token=fx["stop_id"], beam_size=5)
+
+    def best(bt, bl, bs, i):
+        k = int(bs[i].argmax())
+        return bt[i, k, :int(bl[i, k])].tolist()
+
+    bt, bl, bs = (t.cpu() for t in eng.generate(fx["prefix_" + key], p))
+    for i, want in enumerate(fx["beam5_" + key]):
+        assert best(bt, bl, bs, i) == want, (i, want)
+    # ... and images -> captions in one call (ViT tokens -> mapper -> beam search on the device): the prefix carries the
+    # bf16 error of two more networks, so a near-tie of this random-init model may flip
+    bt, bl, bs = (t.cpu() for t in eng.caption_images(fx["images"], p))
+    hits = sum(best(bt, bl, bs, i) == want for i, want in enumerate(fx["beam5_" + key]))
+    assert hits >= 2, hits
+    eng.close()

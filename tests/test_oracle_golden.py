@@ -168,3 +168,28 @@ def test_typical_filtering_matches_reference():
     assert same(orc.typical_filtering(L, tx["typ_rows_p"].clone()), tx["typ_rows"])
     assert same(orc.typical_filtering(orc.top_k_top_p_filtering_batch(L, 0, 0.9), 0.5), tx["topp_0.9_typ_0.5"])
     assert torch.equal(orc.typical_filtering(L, 0.0), L)          # disabled
+
+
+def test_all_vit_features_path_matches_reference():
+    """The fork's default configuration (use_all_vit_features): patched ViT forward (inference.py:421-444) ->
+    TransformerMapperAllFeatures (layers/Transformer.py:164-203) -> CLIPCaptionModel.forward, against the unmodified
+    reference modules."""
+    fx = torch.load(os.path.join(GOLDEN, "tiny_allfeatures.pt"), weights_only=False)
+    f32 = lambda sd: {k: (v.float() if v.is_floating_point() else v) for k, v in sd.items()}
+    toks = orc.vit_forward(f32(fx["sd_vit"]), fx["images"], fx["vit_heads"], fx["vit_patch"], all_tokens=True)
+    assert toks.shape == fx["vit_tokens"].shape == (3, fx["T"], fx["dim_clip"])
+    assert (toks - fx["vit_tokens"]).abs().max().item() <= 1e-4 * fx["vit_tokens"].abs().max().item()
+    lm = orc.OracleLM(f32(fx["sd_lm"]), "gpt2", fx["heads"])
+    for key in ("pos", "nopos"):
+        sd = f32(fx["sd_mapper_" + key])
+        assert ("pos_embeddings" in sd) == (key == "pos")
+        prefix = orc.mapper_all_forward(sd, fx["vit_tokens"], fx["map_heads"], "relu")
+        assert (prefix - fx["prefix_" + key]).abs().max().item() <= 1e-4 * fx["prefix_" + key].abs().max().item()
+        emb = torch.cat((prefix, lm.get_embedding_text(fx["cap_tokens"])), dim=1)
+        logits = lm.logits(emb)
+        ref = fx["forward_logits_" + key]
+        assert (logits - ref).abs().max().item() <= 1e-3 * ref.abs().max().item()
+        for i, want in enumerate(fx["beam5_" + key]):
+            t, l, sc, order = orc.generate_beam(lm, fx["prefix_" + key][i:i + 1], beam_size=5, entry_length=10, stop_token=fx["stop_id"])
+            best = t[order[0]][:int(l[order[0]])].tolist()
+            assert best == want, (key, i, best, want)

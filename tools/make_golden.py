@@ -230,6 +230,65 @@ def make_typical_fixture(ref, seed):
     return fx
 
 
+def make_allfeatures_fixture(ref, seed):
+    """The fork's default configuration (train.py:73 use_all_vit_features=True): every projected ViT token
+    (the patched VisionTransformer.forward of inference.py:421-444; HF CLIPVisionModelWithProjection stands in for the
+    un-installed OpenAI clip: tokens = last_hidden_state @ visual_projection^T, no post_layernorm) ->
+    layers.TransformerMapperAllFeatures (layers/Transformer.py:164-203) with and without pos_embeddings ->
+    CLIPCaptionModel.forward / generate_beam of the UNMODIFIED reference."""
+    from transformers import CLIPVisionConfig, CLIPVisionModelWithProjection, GPT2Config
+    torch.manual_seed(seed)
+    V, d, heads, P, dim_clip = 503, 128, 2, 4, 64
+    vit_cfg = CLIPVisionConfig(hidden_size=64, intermediate_size=256, num_hidden_layers=2, num_attention_heads=2,
+                               image_size=64, patch_size=32, projection_dim=dim_clip, hidden_act="quick_gelu")
+    vit = bf16_round_(CLIPVisionModelWithProjection(vit_cfg).eval())
+    T = (64 // 32) ** 2 + 1
+    lm = ref.lms.GPT2(GPT2Config(vocab_size=V, n_positions=64, n_embd=d, n_layer=2, n_head=heads))
+    with torch.no_grad():
+        lm.transformer.wte.weight.mul_(4.0)
+        for n_, p_ in lm.transformer.h.named_parameters():
+            if p_.dim() == 2:
+                p_.mul_(6.0)
+    lm = bf16_round_(lm.eval())
+    tok = TokenizerStub(13, bos=V - 1, special=[V - 1])
+
+    class VisualTokens(torch.nn.Module):   # what clip_model.visual.forward returns after the fork's patch
+        def __init__(self, m):
+            super().__init__()
+            self.m = m
+
+        def forward(self, x):
+            h = self.m.vision_model(pixel_values=x).last_hidden_state
+            return self.m.visual_projection(h)
+
+    fx = {"V": V, "d": d, "heads": heads, "P": P, "T": T, "dim_clip": dim_clip, "map_heads": 8, "vit_heads": 2, "vit_patch": 32,
+          "vit_image": 64, "vit_width": 64, "vit_layers": 2, "stop_id": 13}
+    images = torch.randn(3, 3, 64, 64)
+    fx["images"] = images
+    fx["sd_lm"] = pack_sd(lm.state_dict())
+    fx["sd_vit"] = pack_sd(export_clip_vision(vit))
+    for pos in (True, False):
+        model = ref.model.CLIPCaptionModel(
+            language_model=lm, tokenizer=tok, visual_encoder=VisualTokens(vit), validator=None, train_visual_encoder=False,
+            use_all_vit_features=True, prefix_size=dim_clip, prefix_length=P, clip_prefix_length=T, num_attention_heads=8,
+            num_layers=2, mlp_ratio=4.0, prefix_init_std=1.0, act_fn_name="relu", pos_embeddings=pos)
+        bf16_round_(model.clip_project)
+        model.eval()
+        key = "pos" if pos else "nopos"
+        with torch.no_grad():
+            tokens_feat = model.visual_encoder(images).float()
+            prefix = model.clip_project(tokens_feat)
+            fx["vit_tokens"] = tokens_feat
+            fx["prefix_" + key] = prefix
+            cap = torch.randint(0, V, (3, 6))
+            fx["cap_tokens"] = cap if "cap_tokens" not in fx else fx["cap_tokens"]
+            fx["forward_logits_" + key] = model(fx["cap_tokens"], tokens_feat, torch.ones(3, 6, dtype=torch.bool)).logits
+            fx["beam5_" + key] = [ref.inference.generate_beam(model, tok, prefix[i:i + 1], beam_size=5, entry_length=10)[0]
+                                  for i in range(3)]
+        fx["sd_mapper_" + key] = pack_sd(model.clip_project.state_dict())
+    return fx
+
+
 def main():
     ref = ref_harness.load_reference()
     os.makedirs(OUT, exist_ok=True)
@@ -245,6 +304,11 @@ def main():
         path = os.path.join(OUT, "sampler.pt")
         torch.save(fx, path)
         print(path, os.path.getsize(path) // 1024, "KiB")
+    if "--only-typical" not in sys.argv or "--allfeatures" in sys.argv:
+        fx = make_allfeatures_fixture(ref, 23)
+        path = os.path.join(OUT, "tiny_allfeatures.pt")
+        torch.save(fx, path)
+        print(path, os.path.getsize(path) // 1024, "KiB", fx["beam5_pos"], fx["beam5_nopos"])
     fx = make_typical_fixture(ref, 22)
     path = os.path.join(OUT, "typical.pt")
     torch.save(fx, path)

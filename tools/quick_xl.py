@@ -10,7 +10,8 @@ mode = sys.argv[2] if len(sys.argv) > 2 else "greedy"
 T = int(sys.argv[3]) if len(sys.argv) > 3 else 32
 iters = int(sys.argv[4]) if len(sys.argv) > 4 else 4
 beam = 5 if mode == "beam" else 1
-cfg = cc.EngineConfig(max_images=B, max_beam=beam, max_ctx=80)
+all_feats = len(sys.argv) > 5 and sys.argv[5] == "all"   # use_all_vit_features: 50 ViT tokens -> TransformerMapperAllFeatures
+cfg = cc.EngineConfig(max_images=B, max_beam=beam, max_ctx=80, **(dict(map_kind="transformer_all", map_clip_len=50) if all_feats else {}))
 t0 = time.time()
 eng = cc.Engine(cfg)
 sds = synthetic.load_synthetic(eng)
