@@ -203,7 +203,8 @@ __global__ void __launch_bounds__(192, GemmCfg<BN>::kMinBlocks) gemm_bf16_tn_ker
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  constexpr uint32_t kDataBytes = kStages * Cfg::kStageBytes + (Cfg::kSeparateStaging ? Cfg::kStagingBytes : 0);
+  // (the separate split-K staging area exists only in split-K launches: see the launcher)
+  const uint32_t kDataBytes = kStages * Cfg::kStageBytes + ((Cfg::kSeparateStaging && p.split_k > 1) ? Cfg::kStagingBytes : 0);
   const uint32_t bar_base = smem_base + kDataBytes;
   // barrier layout: full[kStages], empty[kStages], tmem_full, then the TMEM address slot
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
