@@ -45,6 +45,8 @@ PROTOTYPES = {
     "ccb_device_bytes": (_L, [_P]),
     "ccb_load_weight": (_I, [_P, C.c_char_p, _P, _I, C.POINTER(_L), _I, _P]),
     "ccb_weights_complete": (_I, [_P]),
+    "ccb_preprocess_scratch_bytes": (_L, [_I, _I, _I, _I, _I]),
+    "ccb_preprocess_image": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, C.POINTER(_F), C.POINTER(_F), _P, _P, _L, _P]),
     "ccb_vit_encode": (_I, [_P, _P, _I, _I, _P, _P]),
     "ccb_vit_encode_tokens": (_I, [_P, _P, _I, _I, _P, _P]),
     "ccb_map_prefix": (_I, [_P, _P, _I, _P, _P]),

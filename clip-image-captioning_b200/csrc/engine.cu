@@ -990,6 +990,21 @@ int ccb_weights_complete(ccb_ctx* c) {
   return 0;
 }
 
+int64_t ccb_preprocess_scratch_bytes(int H, int W, int new_h, int new_w, int n_px) {
+  return static_cast<int64_t>(preprocess_scratch_bytes(H, W, new_h, new_w, n_px));
+}
+
+int ccb_preprocess_image(ccb_ctx* c, const uint8_t* rgb_hwc, int H, int W, int new_h, int new_w, int crop_top, int crop_left,
+                         int n_px, const float* mean3, const float* std3, float* out_chw, void* scratch, int64_t scratch_bytes,
+                         void* stream) {
+  if (!c || !rgb_hwc || !mean3 || !std3 || !out_chw || !scratch) return fail(c, "ccb_preprocess_image: null argument");
+  const int r = preprocess_image(rgb_hwc, H, W, new_h, new_w, crop_top, crop_left, n_px, mean3, std3, out_chw, scratch,
+                                 static_cast<size_t>(scratch_bytes), static_cast<cudaStream_t>(stream));
+  if (r != 0) return fail(c, "ccb_preprocess_image: bad geometry / scratch too small / launch failed (%d)", r);
+  c->launches += (new_h == H && new_w == W) ? 1 : 4;
+  return 0;
+}
+
 int ccb_vit_encode(ccb_ctx* c, const void* images, int dtype, int B, float* feat_out, void* stream) {
   if (!c || !images || !feat_out) return fail(c, "ccb_vit_encode: null argument");
   return vit_forward(c, images, dtype, B, feat_out, static_cast<cudaStream_t>(stream));

@@ -108,6 +108,11 @@ int convert_rows_bf16(const void* src, int dtype, long long rows, int cols, bf16
 int convert_f32(const void* src, int dtype, long long n, float* dst, cudaStream_t s);
 int transpose_bf16(const void* src, int dtype, int R, int C, bf16* dst /*[C, R]*/, long long dst_ld, cudaStream_t s);
 
+// ------------------------------------------------------------------ image preprocessing (preprocess.cu)
+size_t preprocess_scratch_bytes(int H, int W, int new_h, int new_w, int n_px);
+int preprocess_image(const uint8_t* rgb, int H, int W, int new_h, int new_w, int top, int left, int n_px, const float* mean,
+                     const float* stdv, float* out, void* scratch, size_t scratch_bytes, cudaStream_t s);
+
 // ------------------------------------------------------------------ attention (attention.cu)
 struct KvCache {
   bf16* base = nullptr;     // [L][2][num_pages][H][page_tokens][hd]

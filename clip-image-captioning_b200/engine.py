@@ -176,6 +176,40 @@ class Engine:
     def check_weights(self):
         self._check(self.lib.ccb_weights_complete(self._h))
 
+    # ------------------------------------------------------------------------------------------ preprocessing
+    CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)   # clip/clip.py _transform
+    CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
+
+    @staticmethod
+    def resize_geometry(h: int, w: int, n_px: int):
+        """(new_h, new_w, crop_top, crop_left) of Resize(n_px) + CenterCrop(n_px) exactly as torchvision computes them."""
+        short, long = (w, h) if w <= h else (h, w)
+        new_short, new_long = n_px, int(n_px * long / short)
+        new_w, new_h = (new_short, new_long) if w <= h else (new_long, new_short)
+        return new_h, new_w, int(round((new_h - n_px) / 2.0)), int(round((new_w - n_px) / 2.0))
+
+    def preprocess_images(self, images, n_px: Optional[int] = None, mean=None, std=None) -> torch.Tensor:
+        """CLIP's `_transform` on the device: a list of decoded RGB images (uint8 tensors [H, W, 3], any sizes) ->
+        [B, 3, n_px, n_px] f32, bit-identical to Resize(n_px, BICUBIC) -> CenterCrop -> ToTensor -> Normalize on PIL images."""
+        n_px = n_px or self.cfg.vit_image
+        mean = (C.c_float * 3)(*(mean or self.CLIP_MEAN))
+        std = (C.c_float * 3)(*(std or self.CLIP_STD))
+        out = torch.empty(len(images), 3, n_px, n_px, device=self.device, dtype=torch.float32)
+        held = []
+        for i, im in enumerate(images):
+            im = self._dev(im, torch.uint8).contiguous()
+            if im.dim() != 3 or im.shape[2] != 3:
+                raise ValueError("images must be uint8 [H, W, 3]")
+            h, w = int(im.shape[0]), int(im.shape[1])
+            nh, nw, top, left = self.resize_geometry(h, w, n_px)
+            nbytes = int(self.lib.ccb_preprocess_scratch_bytes(h, w, nh, nw, n_px))
+            scratch = torch.empty(nbytes, device=self.device, dtype=torch.uint8)
+            self._check(self.lib.ccb_preprocess_image(self._h, _ptr(im), h, w, nh, nw, top, left, n_px, mean, std, _ptr(out[i]),
+                                                      _ptr(scratch), nbytes, self._stream()))
+            held += [im, scratch]
+        self._keep = held
+        return out
+
     # ------------------------------------------------------------------------------------------ stages
     def vit_encode(self, images: torch.Tensor, all_tokens: Optional[bool] = None) -> torch.Tensor:
         """[B, vit_out] (CLS token through ln_post and proj), or with all_tokens (default for the "transformer_all"

@@ -99,6 +99,18 @@ CCB_API int ccb_load_weight(ccb_ctx* ctx, const char* name, const void* dev_ptr,
 /* 0 when every weight the context needs has been loaded; otherwise -1 and ccb_last_error names one missing */
 CCB_API int ccb_weights_complete(ccb_ctx* ctx);
 
+/* ---- the step in front of the path: CLIP's image preprocessing ------------------------------------------ */
+/* `clip_preprocess(image)` (clip.load(...)[1] = Compose([Resize(n_px, BICUBIC), CenterCrop(n_px), ToTensor, Normalize]);
+ * applied at inference.py:310, evaluate_model.py:458-463; the same pipeline as blip_test.py:22-26) for ONE decoded RGB
+ * image already on the device: rgb_hwc uint8 [H, W, 3] -> out_chw f32 [3, n_px, n_px].  PIL's antialiased bicubic resize
+ * is reproduced exactly (Pillow Resample.c: double-precision coefficients rounded to 22-bit fixed point, uint8 between the
+ * two passes).  The caller supplies the geometry exactly as torchvision computes it: the resized size (new_h, new_w) and
+ * the crop origin.  mean3 / std3 are HOST pointers.  scratch: device memory of ccb_preprocess_scratch_bytes(...) bytes. */
+CCB_API int64_t ccb_preprocess_scratch_bytes(int H, int W, int new_h, int new_w, int n_px);
+CCB_API int ccb_preprocess_image(ccb_ctx* ctx, const uint8_t* rgb_hwc, int H, int W, int new_h, int new_w, int crop_top,
+                                 int crop_left, int n_px, const float* mean3, const float* std3, float* out_chw, void* scratch,
+                                 int64_t scratch_bytes, void* stream);
+
 /* ---- the hot path, stage by stage ---------------------------------------------------------------------- */
 /* clip_model.encode_image(image) (inference.py:311) / model.visual_encoder(image_tensor)
  * (evaluate_model.py:359): images [B,3,H,W] NCHW -> feat_out [B, vit_out] f32 */
