@@ -23,7 +23,8 @@ class ModelDesc(C.Structure):
             "map_kind", "map_dim_clip", "map_clip_len", "map_prefix_len", "map_heads", "map_layers", "map_hidden",
             "map_act",
             "vit_present", "vit_image", "vit_patch", "vit_width", "vit_layers", "vit_heads", "vit_out",
-            "max_images", "max_beam", "max_ctx", "max_lm_tokens", "page_tokens")]
+            "max_images", "max_beam", "max_ctx", "max_lm_tokens", "page_tokens",
+            "text_present", "text_vocab", "text_ctx", "text_width", "text_layers", "text_heads", "text_out", "max_texts")]
 
 
 class GenParams(C.Structure):
@@ -49,6 +50,7 @@ PROTOTYPES = {
     "ccb_preprocess_image": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, C.POINTER(_F), C.POINTER(_F), _P, _P, _L, _P]),
     "ccb_vit_encode": (_I, [_P, _P, _I, _I, _P, _P]),
     "ccb_vit_encode_tokens": (_I, [_P, _P, _I, _I, _P, _P]),
+    "ccb_clip_encode_text": (_I, [_P, _P, _I, _P, _P]),
     "ccb_map_prefix": (_I, [_P, _P, _I, _P, _P]),
     "ccb_embed_tokens": (_I, [_P, _P, _I, _P, _P]),
     "ccb_lm_forward": (_I, [_P, _P, _I, _I, _P, _P, _L, _I, _P]),

@@ -274,6 +274,57 @@ int vit_forward(ccb_ctx* c, const void* images, int dtype, int B, float* feat_ou
   return 0;
 }
 
+// positions r % ctx and, per sequence, the index of its largest token id (the end-of-text token, OpenAI clip/model.py:
+// `x[torch.arange(x.shape[0]), text.argmax(dim=-1)]`; the first maximum wins like torch.argmax)
+__global__ void text_positions_eot_kernel(const int* __restrict__ tokens, int ctx, int* __restrict__ positions, int* __restrict__ eot) {
+  const int b = blockIdx.x;
+  for (int t = threadIdx.x; t < ctx; t += blockDim.x) positions[b * ctx + t] = t;
+  if (threadIdx.x == 0) {
+    int best = 0, bv = tokens[b * ctx];
+    for (int t = 1; t < ctx; ++t) {
+      const int v = tokens[b * ctx + t];
+      if (v > bv) {
+        bv = v;
+        best = t;
+      }
+    }
+    eot[b] = best;
+  }
+}
+// dst[b, :] = src[b * ctx + eot[b], :]
+__global__ void gather_eot_rows_kernel(const float* __restrict__ src, const int* __restrict__ eot, int ctx, int d, float* __restrict__ dst) {
+  const int b = blockIdx.x;
+  const float* s = src + (static_cast<long long>(b) * ctx + eot[b]) * d;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) dst[static_cast<long long>(b) * d + c] = s[c];
+}
+
+// CLIP.encode_text (OpenAI clip/model.py; call sites sampling.py:31, evaluate_model.py ClipScoring): token + positional
+// embedding -> causal transformer (QuickGELU) -> ln_final -> row of the end-of-text token @ text_projection
+int text_forward(ccb_ctx* c, const int32_t* tokens, int B, float* feat_out, cudaStream_t s) {
+  const ccb_model_desc& D = c->desc;
+  if (!D.text_present) return fail(c, "context was created without a CLIP text tower");
+  if (B <= 0 || B > D.max_texts) return fail(c, "clip_encode_text: B=%d outside [1, max_texts=%d]", B, D.max_texts);
+  const int w = D.text_width, S = D.text_ctx, M = B * S, H = D.text_heads, hd = w / H;
+  text_positions_eot_kernel<<<B, 128, 0, s>>>(tokens, S, c->txt_positions, c->txt_eot);
+  RUN(launch_check());
+  RUN(embed_tokens(c->txt_wte, c->txt_wpe, tokens, c->txt_positions, c->h, M, w, s));
+  BlockShape sh{w, 4 * w, CCB_ACT_QUICKGELU, 1e-5f, false};
+  const float scale = 1.0f / sqrtf(static_cast<float>(hd));
+  for (int l = 0; l < D.text_layers; ++l) {
+    auto attn = [&]() {
+      return attention_prefill(c->qkv, c->att, B, S, H, hd, scale, 1, nullptr, 0, nullptr, 0, 0, nullptr, s);
+    };
+    if (block_forward(c, c->txt[l], M, sh, attn, s)) return -1;
+  }
+  // ln_final is row-wise: gathering the end-of-text rows first is the same arithmetic on B instead of B * ctx rows
+  float* rows = reinterpret_cast<float*>(c->mlp);   // [B, w] f32 scratch (the MLP buffer is free here)
+  gather_eot_rows_kernel<<<B, 256, 0, s>>>(c->h, c->txt_eot, S, w, rows);
+  RUN(launch_check());
+  RUN(layernorm_f32_bf16(rows, w, c->txt_ln_final.g, c->txt_ln_final.b, 1e-5f, c->x, w, B, w, s));
+  RUN(linear(c, c->x, w, B, c->txt_proj, CCB_ACT_NONE, nullptr, 0, feat_out, D.text_out, 0, s));
+  return 0;
+}
+
 // feat [B, dim_clip] f32 -> out [B, out_rows_per_image, d] rows [0, P) (out_rows_per_image >= P)
 int map_forward(ccb_ctx* c, const float* feat, int B, float* out, int out_rows_per_image, cudaStream_t s) {
   const ccb_model_desc& D = c->desc;
@@ -681,6 +732,10 @@ int ccb_create(ccb_ctx** out, const ccb_model_desc* desc, int device) {
   if (D.vit_present && (D.vit_width % 64 || D.vit_width % D.vit_heads || D.vit_image % D.vit_patch || D.vit_patch % 8))
     return fail(nullptr, "ccb_create: bad ViT dimensions");
 
+  if (D.text_present && (D.text_width % 64 || D.text_heads <= 0 || D.text_width % D.text_heads || (D.text_width / D.text_heads) % 16 ||
+                         D.text_ctx <= 0 || D.text_ctx > 128 || D.text_vocab <= 0 || D.text_out <= 0 || D.max_texts <= 0))
+    return fail(nullptr, "ccb_create: bad CLIP text-tower dimensions");
+
   ccb_ctx* c = new ccb_ctx();
   c->desc = D;
   c->device = device;
@@ -824,14 +879,50 @@ int ccb_create(ccb_ctx** out, const ccb_model_desc* desc, int device) {
     add_slot(c, "visual.proj", WeightSlot::MATRIX_T, c->vit_proj.w, w, D.vit_out, w);  // proj [w, out] -> [out, w]
   }
 
+  // ---- CLIP text tower (OpenAI names under "clip_text.": token_embedding.weight, positional_embedding,
+  //      transformer.resblocks.N.*, ln_final.*, text_projection)
+  if (D.text_present) {
+    const int w = D.text_width;
+    c->txt_wte = a.arr<bf16>(static_cast<size_t>(D.text_vocab) * w);
+    c->txt_wpe = a.arr<bf16>(static_cast<size_t>(D.text_ctx) * w);
+    add_slot(c, "clip_text.token_embedding.weight", WeightSlot::ROWS_BF16, c->txt_wte, D.text_vocab, w, w);
+    add_slot(c, "clip_text.positional_embedding", WeightSlot::ROWS_BF16, c->txt_wpe, D.text_ctx, w, w);
+    make_ln(a, c->txt_ln_final, w);
+    slot_ln(c, "clip_text.ln_final", c->txt_ln_final, w);
+    c->txt.resize(D.text_layers);
+    for (int l = 0; l < D.text_layers; ++l) {
+      Block& b = c->txt[l];
+      const std::string base = fmt("clip_text.transformer.resblocks.%d", l);
+      make_ln(a, b.ln1, w);
+      make_ln(a, b.ln2, w);
+      slot_ln(c, base + ".ln_1", b.ln1, w);
+      slot_ln(c, base + ".ln_2", b.ln2, w);
+      make_linear(c, a, b.qkv, 3 * w, w, true);
+      make_linear(c, a, b.proj, w, w, true);
+      make_linear(c, a, b.fc, 4 * w, w, true);
+      make_linear(c, a, b.fc2, w, 4 * w, true);
+      add_slot(c, base + ".attn.in_proj_weight", WeightSlot::MATRIX, b.qkv.w, 3 * w, w, w);
+      add_slot(c, base + ".attn.in_proj_bias", WeightSlot::VECTOR_F32, b.qkv.bias, 3 * w, 1, 1);
+      slot_linear(c, base + ".attn.out_proj", b.proj);
+      slot_linear(c, base + ".mlp.c_fc", b.fc);
+      slot_linear(c, base + ".mlp.c_proj", b.fc2);
+    }
+    make_linear(c, a, c->txt_proj, D.text_out, w, false);
+    add_slot(c, "clip_text.text_projection", WeightSlot::MATRIX_T, c->txt_proj.w, w, D.text_out, w);  // [w, out] -> [out, w]
+    c->txt_positions = a.arr<int>(static_cast<size_t>(D.max_texts) * D.text_ctx);
+    c->txt_eot = a.arr<int>(D.max_texts);
+  }
+
   // ---- workspaces
   c->max_rows = D.max_images * D.max_beam;
   int M = std::max(D.max_lm_tokens, c->max_rows);
   M = std::max(M, D.max_images * map_S);
   M = std::max(M, D.max_images * vit_S);
+  if (D.text_present) M = std::max(M, D.max_texts * D.text_ctx);
   c->max_rows_tokens = M;
-  c->dmax = std::max(d, D.vit_present ? D.vit_width : 0);
+  c->dmax = std::max(d, std::max(D.vit_present ? D.vit_width : 0, D.text_present ? D.text_width : 0));
   c->hidden_max = std::max(4 * d, std::max(D.map_kind != CCB_MAP_NONE ? D.map_hidden : 0, D.vit_present ? 4 * D.vit_width : 0));
+  if (D.text_present) c->hidden_max = std::max(c->hidden_max, 4 * D.text_width);
   const size_t Mz = static_cast<size_t>(M);
   c->h = a.arr<float>(Mz * c->dmax);
   c->x = a.arr<bf16>(Mz * c->dmax);
@@ -1013,6 +1104,11 @@ int ccb_vit_encode(ccb_ctx* c, const void* images, int dtype, int B, float* feat
 int ccb_vit_encode_tokens(ccb_ctx* c, const void* images, int dtype, int B, float* tokens_out, void* stream) {
   if (!c || !images || !tokens_out) return fail(c, "ccb_vit_encode_tokens: null argument");
   return vit_forward(c, images, dtype, B, tokens_out, static_cast<cudaStream_t>(stream), true);
+}
+
+int ccb_clip_encode_text(ccb_ctx* c, const int32_t* tokens, int B, float* feat_out, void* stream) {
+  if (!c || !tokens || !feat_out) return fail(c, "ccb_clip_encode_text: null argument");
+  return text_forward(c, tokens, B, feat_out, static_cast<cudaStream_t>(stream));
 }
 
 int ccb_map_prefix(ccb_ctx* c, const float* feat, int B, float* prefix_out, void* stream) {

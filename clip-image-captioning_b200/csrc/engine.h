@@ -81,6 +81,14 @@ struct ccb_ctx {
   ccb::LayerNormW vit_ln_pre, vit_ln_post;
   std::vector<ccb::Block> vit;
   ccb::Linear vit_proj;           // [out, width]
+  // CLIP text tower (re-ranking)
+  ccb::bf16* txt_wte = nullptr;   // token_embedding [vocab, width]
+  ccb::bf16* txt_wpe = nullptr;   // positional_embedding [ctx, width]
+  std::vector<ccb::Block> txt;
+  ccb::LayerNormW txt_ln_final;
+  ccb::Linear txt_proj;           // text_projection [out, width]
+  int* txt_positions = nullptr;   // [max_texts * ctx]: r % ctx
+  int* txt_eot = nullptr;         // [max_texts]: argmax of the token ids of each sequence
 
   // ---- workspaces
   int max_rows_tokens = 0;        // rows of the activation workspaces

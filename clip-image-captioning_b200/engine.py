@@ -46,6 +46,14 @@ class EngineConfig:
     vit_layers: int = 12
     vit_heads: int = 12
     vit_out: int = 512
+    text: bool = False               # CLIP text tower for re-ranking (clip_model.encode_text, sampling.py:31)
+    text_vocab: int = 49408
+    text_ctx: int = 77
+    text_width: int = 512
+    text_layers: int = 12
+    text_heads: int = 8
+    text_out: int = 512
+    max_texts: int = 64
     max_images: int = 64
     max_beam: int = 1
     max_ctx: int = 80
@@ -72,6 +80,9 @@ class EngineConfig:
         d.max_images, d.max_beam, d.max_ctx = self.max_images, self.max_beam, self.max_ctx
         d.max_lm_tokens = self.max_lm_tokens or self.max_images * self.max_ctx
         d.page_tokens = self.page_tokens
+        d.text_present = 1 if self.text else 0
+        d.text_vocab, d.text_ctx, d.text_width = self.text_vocab, self.text_ctx, self.text_width
+        d.text_layers, d.text_heads, d.text_out, d.max_texts = self.text_layers, self.text_heads, self.text_out, self.max_texts
         return d
 
 
@@ -227,6 +238,16 @@ class Engine:
             return out
         out = torch.empty(B, self.cfg.vit_out, device=self.device, dtype=torch.float32)
         self._check(self.lib.ccb_vit_encode(self._h, _ptr(images), _TORCH_DTYPE[images.dtype], B, _ptr(out), self._stream()))
+        return out
+
+    def clip_encode_text(self, tokens: torch.Tensor) -> torch.Tensor:
+        """clip_model.encode_text(tokens) (sampling.py:31): tokens [B, text_ctx] (clip.tokenize ids; the end-of-text token is
+        the largest id) -> [B, text_out] f32, un-normalised."""
+        tk = self._dev(tokens, torch.int32)
+        if tk.dim() != 2 or tk.shape[1] != self.cfg.text_ctx:
+            raise ValueError("tokens must be [B, %d]" % self.cfg.text_ctx)
+        out = torch.empty(tk.shape[0], self.cfg.text_out, device=self.device, dtype=torch.float32)
+        self._check(self.lib.ccb_clip_encode_text(self._h, _ptr(tk), tk.shape[0], _ptr(out), self._stream()))
         return out
 
     def map_prefix(self, feat: torch.Tensor) -> torch.Tensor:

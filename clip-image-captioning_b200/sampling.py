@@ -87,3 +87,20 @@ def typical_filtering(logits: torch.Tensor, typ_p: Union[float, torch.Tensor] = 
     p.q_ld = 0
     out = eng.sample(L, p, return_filtered=True)[1]
     return out[0] if squeeze else out
+
+
+def cos_sim(a: torch.Tensor, b: torch.Tensor, normalize: bool = True) -> torch.Tensor:
+    """sampling.py:14-18."""
+    if normalize:
+        a = a / torch.norm(a, dim=-1, keepdim=True)
+        b = b / torch.norm(b, dim=-1, keepdim=True)
+    return a @ b.T
+
+
+def clip_rank(engine: Engine, image: torch.Tensor, text_tokens: torch.Tensor):
+    """sampling.py:21-37 on the device: cosine similarity of every candidate caption with the image, both towers on the
+    engine.  `image`: one preprocessed image [3, H, W] (Engine.preprocess_images) ; `text_tokens`: [n, 77] ids from
+    clip.tokenize (the tokenizer itself is host code and stays the caller's).  Returns a list of n floats."""
+    image_features = engine.vit_encode(image.unsqueeze(0) if image.dim() == 3 else image, all_tokens=False)
+    text_features = engine.clip_encode_text(text_tokens)
+    return cos_sim(text_features, image_features).reshape(-1).tolist()

@@ -122,6 +122,30 @@ def vit_state_dict(cfg: EngineConfig, seed: int = 1236, device="cpu"):
     return sd
 
 
+def text_state_dict(cfg: EngineConfig, seed: int = 1237, device="cpu"):
+    """OpenAI CLIP text-tower names; scales follow CLIP.initialize_parameters."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    w, L = cfg.text_width, cfg.text_layers
+    sd = {"token_embedding.weight": _rn(g, (cfg.text_vocab, w), 0.02, device),
+          "positional_embedding": _rn(g, (cfg.text_ctx, w), 0.01, device),
+          "text_projection": _rn(g, (w, cfg.text_out), w ** -0.5, device)}
+    _ln(sd, "ln_final", w, device)
+    attn_std, proj_std, fc_std = w ** -0.5, (w ** -0.5) * ((2 * L) ** -0.5), (2 * w) ** -0.5
+    for l in range(L):
+        p = "transformer.resblocks.%d." % l
+        _ln(sd, p + "ln_1", w, device)
+        _ln(sd, p + "ln_2", w, device)
+        sd[p + "attn.in_proj_weight"] = _rn(g, (3 * w, w), attn_std, device)
+        sd[p + "attn.in_proj_bias"] = torch.zeros(3 * w, device=device)
+        sd[p + "attn.out_proj.weight"] = _rn(g, (w, w), proj_std, device)
+        sd[p + "attn.out_proj.bias"] = torch.zeros(w, device=device)
+        sd[p + "mlp.c_fc.weight"] = _rn(g, (4 * w, w), fc_std, device)
+        sd[p + "mlp.c_fc.bias"] = torch.zeros(4 * w, device=device)
+        sd[p + "mlp.c_proj.weight"] = _rn(g, (w, 4 * w), proj_std, device)
+        sd[p + "mlp.c_proj.bias"] = torch.zeros(w, device=device)
+    return sd
+
+
 def synthetic_images(n: int, cfg: EngineConfig, seed: int = 0, device="cpu", dtype=torch.float32):
     """randn images in the already-normalised space of CLIP's preprocessing."""
     g = torch.Generator(device=device).manual_seed(seed)
@@ -141,5 +165,8 @@ def load_synthetic(engine, seed: int = 1234, device=None, **lm_kwargs):
     if cfg.vit:
         sds["vit"] = vit_state_dict(cfg, seed + 2, device)
         engine.load_state_dict(sds["vit"], prefix="visual.")
+    if getattr(cfg, "text", False):
+        sds["text"] = text_state_dict(cfg, seed + 3, device)
+        engine.load_state_dict(sds["text"], prefix="clip_text.")
     engine.check_weights()
     return sds

@@ -58,6 +58,10 @@ typedef struct ccb_model_desc {
   int32_t max_ctx;         /* prefix + generated tokens per sequence */
   int32_t max_lm_tokens;   /* max B*S of one ccb_lm_forward call */
   int32_t page_tokens;     /* KV page size for greedy / sampling (beam search uses token-granular pages) */
+  /* CLIP text tower for re-ranking (clip_model.encode_text: sampling.py:31, evaluate_model.py:182-352; OpenAI
+   * clip/model.py CLIP.encode_text): vocab 49408, context 77, width 512, 12 layers, 8 heads, output 512 for ViT-B/32 */
+  int32_t text_present, text_vocab, text_ctx, text_width, text_layers, text_heads, text_out;
+  int32_t max_texts;       /* token sequences per ccb_clip_encode_text call */
 } ccb_model_desc;
 
 typedef struct ccb_gen_params {
@@ -118,6 +122,10 @@ CCB_API int ccb_vit_encode(ccb_ctx* ctx, const void* images, int dtype, int B, f
 /* the patched VisionTransformer.forward of the all-features path (inference.py:421-444, evaluate_model.py: same patch):
  * no ln_post / CLS extraction, every token projected: images [B,3,H,W] -> tokens_out [B, 1 + (H/patch)^2, vit_out] f32 */
 CCB_API int ccb_vit_encode_tokens(ccb_ctx* ctx, const void* images, int dtype, int B, float* tokens_out, void* stream);
+/* clip_model.encode_text(clip.tokenize(txt)) (sampling.py:30-31; OpenAI clip/model.py CLIP.encode_text): tokens [B, text_ctx]
+ * int32 (the end-of-text token has the highest id, its position is where the features are read) -> feat_out [B, text_out]
+ * f32, un-normalised like the reference (cos_sim, sampling.py:14-18, normalises). */
+CCB_API int ccb_clip_encode_text(ccb_ctx* ctx, const int32_t* tokens, int B, float* feat_out, void* stream);
 /* model.clip_project(prefix) (inference.py:312, model.py:137; layers/Transformer.py:153-161):
  * feat [B, map_dim_clip] f32 -> prefix_out [B, map_prefix_len, lm_d] f32.  With CCB_MAP_TRANSFORMER_ALL
  * (layers/Transformer.py:186-203) feat is [B, map_clip_len, map_dim_clip], the output of ccb_vit_encode_tokens. */

@@ -126,6 +126,41 @@ def mlp_mapper_forward(sd: SD, feat: torch.Tensor, prefix_length: int) -> torch.
     return F.linear(h, sd["model.2.weight"], sd["model.2.bias"]).view(feat.shape[0], prefix_length, -1)
 
 
+def clip_text_forward(sd: SD, tokens: torch.Tensor, heads: int) -> torch.Tensor:
+    """CLIP.encode_text of OpenAI clip (clip/model.py, pinned nowhere in the reference tree: `clip` is an unpinned git
+    dependency, requirements.txt; call sites sampling.py:31, evaluate_model.py ClipScoring): token_embedding +
+    positional_embedding -> causal pre-LN transformer with QuickGELU -> ln_final -> features at the end-of-text token
+    (the arg-max token id) @ text_projection.  `sd` uses the OpenAI names."""
+    x = sd["token_embedding.weight"][tokens] + sd["positional_embedding"]
+    B, S, w = x.shape
+    hd = w // heads
+    n_layers = 1 + max(int(k.split(".")[2]) for k in sd if k.startswith("transformer.resblocks."))
+    causal = torch.ones(S, S, dtype=torch.bool, device=x.device).tril()
+    for l in range(n_layers):
+        p = "transformer.resblocks.%d." % l
+        y = F.layer_norm(x, (w,), sd[p + "ln_1.weight"], sd[p + "ln_1.bias"], 1e-5)
+        qkv = F.linear(y, sd[p + "attn.in_proj_weight"], sd[p + "attn.in_proj_bias"])
+        q, k, v = (t.view(B, S, heads, hd).transpose(1, 2) for t in qkv.split(w, dim=2))
+        att = (q @ k.transpose(-1, -2)) / math.sqrt(hd)
+        att = att.masked_fill(~causal, float("-inf")).softmax(-1)
+        a = (att @ v).transpose(1, 2).reshape(B, S, w)
+        x = x + F.linear(a, sd[p + "attn.out_proj.weight"], sd[p + "attn.out_proj.bias"])
+        y = F.layer_norm(x, (w,), sd[p + "ln_2.weight"], sd[p + "ln_2.bias"], 1e-5)
+        y = quick_gelu(F.linear(y, sd[p + "mlp.c_fc.weight"], sd[p + "mlp.c_fc.bias"]))
+        x = x + F.linear(y, sd[p + "mlp.c_proj.weight"], sd[p + "mlp.c_proj.bias"])
+    x = F.layer_norm(x, (w,), sd["ln_final.weight"], sd["ln_final.bias"], 1e-5)
+    x = x[torch.arange(B, device=x.device), tokens.argmax(dim=-1)]
+    return x @ sd["text_projection"]
+
+
+def cos_sim(a, b, normalize=True):
+    """sampling.py:14-18."""
+    if normalize:
+        a = a / torch.norm(a, dim=-1, keepdim=True)
+        b = b / torch.norm(b, dim=-1, keepdim=True)
+    return a @ b.T
+
+
 # ------------------------------------------------------------------------------------------------ GPT-2
 def _causal_attention(q, k, v, key_mask=None, q_offset=0):
     """q [B,H,Sq,hd], k/v [B,H,Sk,hd]; query i sits at absolute position q_offset + i."""

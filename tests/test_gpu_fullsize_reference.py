@@ -126,3 +126,26 @@ def test_beam_search_against_the_reference_loop_at_full_size(full):
     print("beam 5, GPT2-XL: best caption identical for %d / %d images, all five beams for %d / %d" % (same_best, N, same_set, N))
     # random-init log-probabilities are nearly flat, so losing beams swap on near-ties; the winner must hold
     assert same_best >= N - 1
+
+
+def test_clip_text_tower_at_full_size():
+    """CLIP ViT-B/32 text tower (49408 x 512, 77 tokens, 12 layers, 8 heads) against the fp32 oracle on the GPU."""
+    import clipcap_b200 as cc
+    from clipcap_b200 import synthetic
+    cfg = cc.EngineConfig(lm_d=128, lm_layers=1, lm_heads=2, lm_vocab=503, lm_n_pos=64, map_kind="none", vit=False, max_images=4,
+                          max_ctx=32, text=True, max_texts=40)
+    eng = cc.Engine(cfg)
+    sds = synthetic.load_synthetic(eng)
+    g = torch.Generator().manual_seed(3)
+    B = 40
+    tokens = torch.zeros(B, 77, dtype=torch.int64)
+    for b in range(B):
+        n = 2 + (b * 7) % 74
+        tokens[b, 0] = 49406
+        tokens[b, 1:n] = torch.randint(0, 49406, (n - 1,), generator=g)
+        tokens[b, n] = 49407
+    feats = eng.clip_encode_text(tokens)
+    ref = orc.clip_text_forward(sds["text"], tokens.cuda(), cfg.text_heads)
+    assert feats.shape == ref.shape == (B, 512)
+    assert rel(feats, ref) <= TOL
+    eng.close()

@@ -327,3 +327,23 @@ def test_all_vit_features_path(key):
     hits = sum(best(bt, bl, bs, i) == want for i, want in enumerate(fx["beam5_" + key]))
     assert hits >= 2, hits
     eng.close()
+
+
+def test_clip_text_tower_and_ranking():
+    """ccb_clip_encode_text (clip_model.encode_text, sampling.py:31) and the cosine re-ranking of sampling.py:14-37 against
+    the fixture (HF CLIP text model with OpenAI's arg-max pooling + the reference's own cos_sim)."""
+    import clipcap_b200 as cc
+    from clipcap_b200 import sampling as S
+    fx = torch.load(os.path.join(GOLDEN, "tiny_clip_text.pt"), weights_only=False)
+    cfg = cc.EngineConfig(lm_d=128, lm_layers=1, lm_heads=2, lm_vocab=503, lm_n_pos=64, map_kind="none", vit=False, max_images=4,
+                          max_ctx=32, text=True, text_vocab=fx["V"], text_ctx=fx["ctx"], text_width=fx["w"], text_layers=2,
+                          text_heads=fx["heads"], text_out=fx["out"], max_texts=8)
+    eng = cc.Engine(cfg)
+    unused = eng.load_state_dict(fx["sd_text"], prefix="clip_text.")
+    assert not unused
+    feats = eng.clip_encode_text(fx["tokens"])
+    assert rel_err(feats, fx["text_features"]) <= TOL
+    sims = S.cos_sim(feats, fx["image_features"].cuda()).cpu()
+    assert (sims - fx["sims"]).abs().max().item() <= 2e-2
+    assert sims.reshape(-1).argsort().tolist() == fx["sims"].reshape(-1).argsort().tolist()     # same ranking
+    eng.close()

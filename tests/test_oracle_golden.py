@@ -193,3 +193,13 @@ def test_all_vit_features_path_matches_reference():
             t, l, sc, order = orc.generate_beam(lm, fx["prefix_" + key][i:i + 1], beam_size=5, entry_length=10, stop_token=fx["stop_id"])
             best = t[order[0]][:int(l[order[0]])].tolist()
             assert best == want, (key, i, best, want)
+
+
+def test_clip_text_tower_and_cos_sim_match_reference():
+    """encode_text (HF CLIPTextModelWithProjection standing in for the un-installed OpenAI clip) + sampling.cos_sim."""
+    fx = torch.load(os.path.join(GOLDEN, "tiny_clip_text.pt"), weights_only=False)
+    sd = {k: v.float() for k, v in fx["sd_text"].items()}
+    feats = orc.clip_text_forward(sd, fx["tokens"], fx["heads"])
+    assert (feats - fx["text_features"]).abs().max().item() <= 1e-4 * fx["text_features"].abs().max().item()
+    sims = orc.cos_sim(feats, fx["image_features"])
+    assert (sims - fx["sims"]).abs().max().item() <= 1e-5

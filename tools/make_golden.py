@@ -289,6 +289,59 @@ def make_allfeatures_fixture(ref, seed):
     return fx
 
 
+def export_clip_text(hf):
+    """HF CLIPTextModelWithProjection -> OpenAI CLIP text-tower names (token_embedding, positional_embedding,
+    transformer.resblocks.N.*, ln_final, text_projection)."""
+    s = hf.state_dict()
+    o = {"token_embedding.weight": s["text_model.embeddings.token_embedding.weight"],
+         "positional_embedding": s["text_model.embeddings.position_embedding.weight"],
+         "ln_final.weight": s["text_model.final_layer_norm.weight"], "ln_final.bias": s["text_model.final_layer_norm.bias"],
+         "text_projection": s["text_projection.weight"].t().contiguous()}
+    for l in range(hf.config.num_hidden_layers):
+        a = "text_model.encoder.layers.%d." % l
+        b = "transformer.resblocks.%d." % l
+        o[b + "ln_1.weight"], o[b + "ln_1.bias"] = s[a + "layer_norm1.weight"], s[a + "layer_norm1.bias"]
+        o[b + "ln_2.weight"], o[b + "ln_2.bias"] = s[a + "layer_norm2.weight"], s[a + "layer_norm2.bias"]
+        o[b + "attn.in_proj_weight"] = torch.cat([s[a + "self_attn.%s_proj.weight" % n_] for n_ in "qkv"], 0)
+        o[b + "attn.in_proj_bias"] = torch.cat([s[a + "self_attn.%s_proj.bias" % n_] for n_ in "qkv"], 0)
+        o[b + "attn.out_proj.weight"], o[b + "attn.out_proj.bias"] = s[a + "self_attn.out_proj.weight"], s[a + "self_attn.out_proj.bias"]
+        o[b + "mlp.c_fc.weight"], o[b + "mlp.c_fc.bias"] = s[a + "mlp.fc1.weight"], s[a + "mlp.fc1.bias"]
+        o[b + "mlp.c_proj.weight"], o[b + "mlp.c_proj.bias"] = s[a + "mlp.fc2.weight"], s[a + "mlp.fc2.bias"]
+    return {k: v.detach().clone() for k, v in o.items()}
+
+
+def make_clip_text_fixture(ref, seed):
+    """encode_text + cos_sim (sampling.py:14-37).  OpenAI `clip` is not installed: HF CLIPTextModelWithProjection with
+    eos_token_id = 2 (features read at the arg-max token id, exactly OpenAI's rule) stands in for its text tower, the
+    similarity is the reference's own sampling.cos_sim."""
+    from transformers import CLIPTextConfig, CLIPTextModelWithProjection
+    torch.manual_seed(seed)
+    V, ctx, w, heads, out = 131, 16, 64, 2, 32
+    cfg = CLIPTextConfig(vocab_size=V, hidden_size=w, intermediate_size=4 * w, num_hidden_layers=2, num_attention_heads=heads,
+                         max_position_embeddings=ctx, projection_dim=out, hidden_act="quick_gelu", eos_token_id=2,
+                         bos_token_id=0, pad_token_id=1)
+    m = bf16_round_(CLIPTextModelWithProjection(cfg).eval())
+    with torch.no_grad():
+        for n_, p_ in m.named_parameters():
+            if p_.dim() == 2 and "embedding" not in n_:
+                p_.mul_(4.0)
+    m = bf16_round_(m)
+    B = 5
+    tokens = torch.zeros(B, ctx, dtype=torch.int64)
+    for b in range(B):
+        n = 3 + 2 * b
+        tokens[b, 0] = V - 2                                  # start-of-text
+        tokens[b, 1:n] = torch.randint(0, V - 2, (n - 1,))
+        tokens[b, n] = V - 1                                  # end-of-text: the largest id
+    with torch.no_grad():
+        feats = m(input_ids=tokens).text_embeds.float()
+    image_features = torch.randn(1, out)
+    fx = {"V": V, "ctx": ctx, "w": w, "heads": heads, "out": out, "tokens": tokens, "text_features": feats,
+          "image_features": image_features, "sims": ref.sampling.cos_sim(feats, image_features),
+          "sd_text": pack_sd(export_clip_text(m))}
+    return fx
+
+
 def main():
     ref = ref_harness.load_reference()
     os.makedirs(OUT, exist_ok=True)
@@ -304,11 +357,16 @@ def main():
         path = os.path.join(OUT, "sampler.pt")
         torch.save(fx, path)
         print(path, os.path.getsize(path) // 1024, "KiB")
-    if "--only-typical" not in sys.argv or "--allfeatures" in sys.argv:
+    if ("--only-typical" not in sys.argv and "--cliptext" not in sys.argv) or "--allfeatures" in sys.argv:
         fx = make_allfeatures_fixture(ref, 23)
         path = os.path.join(OUT, "tiny_allfeatures.pt")
         torch.save(fx, path)
         print(path, os.path.getsize(path) // 1024, "KiB", fx["beam5_pos"], fx["beam5_nopos"])
+    if "--only-typical" not in sys.argv or "--cliptext" in sys.argv:
+        fx = make_clip_text_fixture(ref, 24)
+        path = os.path.join(OUT, "tiny_clip_text.pt")
+        torch.save(fx, path)
+        print(path, os.path.getsize(path) // 1024, "KiB", fx["sims"].reshape(-1).tolist())
     fx = make_typical_fixture(ref, 22)
     path = os.path.join(OUT, "typical.pt")
     torch.save(fx, path)
