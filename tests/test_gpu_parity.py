@@ -347,3 +347,37 @@ def test_clip_text_tower_and_ranking():
     assert (sims - fx["sims"]).abs().max().item() <= 2e-2
     assert sims.reshape(-1).argsort().tolist() == fx["sims"].reshape(-1).argsort().tolist()     # same ranking
     eng.close()
+
+
+def test_batched_generate_loop_matches_reference(tiny_engine):
+    """sampling.generate (sampling.py:165-268) with the fused sampler kernel per step against the unmodified reference run
+    on the same fake decoder and the same noise stream: identical completion groups, token for token."""
+    import types
+    from clipcap_b200 import sampling as S
+    fx = torch.load(os.path.join(GOLDEN, "sampling_generate.pt"), weights_only=False)
+    E, W = fx["E"], fx["W"]
+
+    class FakeDecoder:   # tools/make_golden.py FakeDecoder (CPU arithmetic on both sides: identical logits)
+        config = types.SimpleNamespace(output_attentions=False, output_hidden_states=False)
+
+        def forward(self, input_ids=None, encoder_hidden_states=None, encoder_attention_mask=None, return_dict=True, **kw):
+            e = E[input_ids.cpu()]
+            prev = torch.cat((e[:, :1] * 0, e[:, :-1]), dim=1)
+            h = e + 0.5 * prev + encoder_hidden_states.cpu().mean(dim=1, keepdim=True)
+            logits = torch.tanh(h) @ W
+            logits[:, :, 3] += 1.2 * torch.arange(logits.shape[1], dtype=logits.dtype).view(1, -1)
+            return {"logits": logits}
+
+    for run in fx["runs"]:
+        torch.manual_seed(run["seed"])
+        kw = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in run["kwargs"].items()}
+        got = S.generate(FakeDecoder(), fx["prompt"].clone(), fx["enc"].clone(), fx["enc_mask"].clone(), eos_token_id=fx["eos"],
+                         engine=tiny_engine, noise_fn=lambda b, v: torch.empty(b, v).exponential_(1), **kw)
+        want = run["results"]
+        assert len(got) == len(want), (len(got), len(want))
+        for g, w in zip(got, want):
+            assert torch.equal(g[0].cpu(), w[0]), (g[0].cpu(), w[0])
+            assert torch.equal(g[1].cpu(), w[1]) and torch.equal(g[2].cpu(), w[2])
+            if torch.is_tensor(w[3]):
+                assert torch.allclose(g[3].cpu(), w[3])
+            assert torch.allclose(g[4].cpu(), w[4], atol=1e-4, rtol=1e-4)

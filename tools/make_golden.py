@@ -12,6 +12,8 @@ weights are exported under the OpenAI names.  The fixtures hold weights + inputs
 consume them (tests/test_oracle_golden.py on CPU, tests/test_gpu_parity.py on the B200) never need the reference.
 """
 import os
+import types
+import math
 import sys
 
 import torch
@@ -342,6 +344,51 @@ def make_clip_text_fixture(ref, seed):
     return fx
 
 
+class FakeDecoder(torch.nn.Module):
+    """A deterministic stand-in for the BLIP text decoder `sampling.generate` drives (no BLIP checkout offline): logits of
+    the last position depend on the last two tokens and on the row's encoder state; no randomness."""
+
+    def __init__(self, E, W):
+        super().__init__()
+        self.E, self.W = E, W
+        self.config = types.SimpleNamespace(output_attentions=False, output_hidden_states=False)
+
+    def forward(self, input_ids=None, encoder_hidden_states=None, encoder_attention_mask=None, return_dict=True, **kw):
+        e = self.E[input_ids.cpu()]
+        prev = torch.cat((e[:, :1] * 0, e[:, :-1]), dim=1)
+        h = e + 0.5 * prev + encoder_hidden_states.cpu().mean(dim=1, keepdim=True)
+        logits = torch.tanh(h) @ self.W
+        logits[:, :, 3] += 1.2 * torch.arange(logits.shape[1], dtype=logits.dtype).view(1, -1)   # EOS (id 3) grows likelier
+        return {"logits": logits}
+
+
+def make_generate_fixture(ref, seed):
+    """sampling.generate (sampling.py:165-268) of the unmodified reference with the fake decoder: per-row budgets, EOS
+    masking before min_length, forced completion on a high EOS probability, alternate-sample fallback."""
+    torch.manual_seed(seed)
+    V, hdim, B, eos = 211, 24, 12, 3
+    E, W = torch.randn(V, hdim), torch.randn(hdim, V) * 1.5
+    dec = FakeDecoder(E, W)
+    enc = torch.randn(B, 5, hdim) * 0.3
+    enc_mask = torch.ones(B, 5, dtype=torch.long)
+    prompt = torch.randint(4, V, (B, 3))
+    fx = {"V": V, "hdim": hdim, "eos": eos, "E": E, "W": W, "enc": enc, "enc_mask": enc_mask, "prompt": prompt, "runs": []}
+    cases = [
+        dict(top_p=torch.linspace(0.3, 0.95, B), top_k=0, typ_p=0.0, min_length=torch.full((B,), 2), max_length=torch.arange(4, 4 + B),
+             repetition_penalty=1.3, min_alternate_prob=0, force_eos_log_prob=math.log(0.9)),
+        dict(top_p=torch.full((B,), 0.9), top_k=torch.tensor([0, 5, 50, 2, 0, 3, 0, 0, 20, 0, 7, 0]), typ_p=torch.linspace(0.2, 0.9, B),
+             min_length=torch.arange(B) % 4, max_length=torch.full((B,), 9), repetition_penalty=None, min_alternate_prob=0.05,
+             force_eos_log_prob=math.log(0.5)),
+        dict(top_p=torch.full((B,), 0.0), top_k=20, typ_p=0.6, min_length=torch.zeros(B, dtype=torch.long),
+             max_length=torch.full((B,), 6), repetition_penalty=1.1, min_alternate_prob=0.2, force_eos_log_prob=1.0),
+    ]
+    for ci, kw in enumerate(cases):
+        torch.manual_seed(1000 + ci)
+        out = ref.sampling.generate(dec, prompt.clone(), enc.clone(), enc_mask.clone(), eos_token_id=eos, **{k: (v.clone() if torch.is_tensor(v) else v) for k, v in kw.items()})
+        fx["runs"].append({"seed": 1000 + ci, "kwargs": kw, "results": [[t.clone() if torch.is_tensor(t) else t for t in grp] for grp in out]})
+    return fx
+
+
 def main():
     ref = ref_harness.load_reference()
     os.makedirs(OUT, exist_ok=True)
@@ -357,16 +404,21 @@ def main():
         path = os.path.join(OUT, "sampler.pt")
         torch.save(fx, path)
         print(path, os.path.getsize(path) // 1024, "KiB")
-    if ("--only-typical" not in sys.argv and "--cliptext" not in sys.argv) or "--allfeatures" in sys.argv:
+    if ("--only-typical" not in sys.argv) or "--allfeatures" in sys.argv:
         fx = make_allfeatures_fixture(ref, 23)
         path = os.path.join(OUT, "tiny_allfeatures.pt")
         torch.save(fx, path)
         print(path, os.path.getsize(path) // 1024, "KiB", fx["beam5_pos"], fx["beam5_nopos"])
-    if "--only-typical" not in sys.argv or "--cliptext" in sys.argv:
+    if ("--only-typical" not in sys.argv) or "--cliptext" in sys.argv:
         fx = make_clip_text_fixture(ref, 24)
         path = os.path.join(OUT, "tiny_clip_text.pt")
         torch.save(fx, path)
         print(path, os.path.getsize(path) // 1024, "KiB", fx["sims"].reshape(-1).tolist())
+    if "--only-typical" not in sys.argv or "--generate" in sys.argv:
+        fx = make_generate_fixture(ref, 25)
+        path = os.path.join(OUT, "sampling_generate.pt")
+        torch.save(fx, path)
+        print(path, os.path.getsize(path) // 1024, "KiB", [[tuple(g[0].shape) for g in r["results"]] for r in fx["runs"]])
     fx = make_typical_fixture(ref, 22)
     path = os.path.join(OUT, "typical.pt")
     torch.save(fx, path)
