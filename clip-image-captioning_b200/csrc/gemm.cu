@@ -287,12 +287,16 @@ int gemm_launch(const GemmArgs& a, const GemmWorkspace& w, cudaStream_t stream) 
   int split = 1;
   if (a.force_split) {
     split = a.force_split;
-  } else if (tiles < w.num_sms) {
-    // fill the machine without spilling into a second wave (one CTA per SM): tiles * split <= number of SMs,
-    // each split >= 4 k-blocks
-    split = w.num_sms / tiles;
-    const int max_by_k = p.k_blocks / 4 > 0 ? p.k_blocks / 4 : 1;
-    if (split > max_by_k) split = max_by_k;
+  } else {
+    // fill the machine without spilling into a second wave: tiles * split <= CTA slots, each split >= 4 k-blocks.
+    // A 32-token tile (3 stages of 20 KB + 48 KB of split-K staging = 109 KB) fits twice on an SM, so the decode GEMMs
+    // of a 16-row GPT-J step run e.g. 96 qkv tiles x 3 splits or 32 out_proj tiles x 8 splits in one wave.
+    const int slots = w.num_sms * (bn == 32 ? 2 : 1);
+    if (tiles < slots) {
+      split = slots / tiles;
+      const int max_by_k = p.k_blocks / 4 > 0 ? p.k_blocks / 4 : 1;
+      if (split > max_by_k) split = max_by_k;
+    }
   }
   if (split > p.k_blocks) split = p.k_blocks;
   if (split > 8) split = 8;  // portable cluster size
