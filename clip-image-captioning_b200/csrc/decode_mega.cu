@@ -600,11 +600,16 @@ __device__ __forceinline__ void init_attn_ctx(const MegaParams& p, ComputeCtx& c
 
 // The X-producer, MMA and TMEM-allocator warps have nothing to do while the attention phase runs: each takes the
 // attention units of one more "compute warp" (11 instead of 8 warps: GPT2-XL x 64 rows = 1600 units on 148 x 11 warps,
-// one unit per warp instead of two for a third of them).  Their K/V staging lies behind the X ring, so they prefetch as
-// soon as they get here; vgo = c_attn complete everywhere, vdone = this warp's outputs are stored.
-__device__ __forceinline__ void helper_attention(const MegaParams& p, ComputeCtx& hc, int cta, int l, uint32_t vgo, uint32_t vdone) {
+// one unit per warp instead of two for a third of them).  Their K/V staging lies behind the X ring (up to ~170 rows), so
+// they prefetch as soon as they get here; vgo = c_attn complete everywhere, vdone = this warp's outputs are stored.
+__device__ __forceinline__ void helper_attention(const MegaParams& p, ComputeCtx& hc, int cta, int l, uint32_t vgo, uint32_t vdone,
+                                                 bool early_prefetch) {
   const float* bias = p.layers[l].b_qkv;
-  attention_phase(p, hc, cta, l, bias, true);
+  // The helpers get here while this CTA's c_attn MMAs may still be reading the X ring.  Their K/V staging (slices 8..10
+  // of the vector scratch, 64..88 KB from the ring's start) lies behind the ring only while the ring is <= 64 KB; above
+  // ~170 rows (three tiles of > 21 KB) it is inside it, and an early prefetch would overwrite live activation tiles
+  // (seen as run-to-run differences of sampled / beam captions at >= 200 rows): then the copies start after vgo.
+  if (early_prefetch) attention_phase(p, hc, cta, l, bias, true);
   ptx::mbar_wait(vgo, static_cast<uint32_t>(l) & 1u);
   attention_phase(p, hc, cta, l, bias, false);
   fence_proxy_async_all();   // att rows are fetched by other CTAs through TMA
@@ -769,6 +774,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const __grid_c
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   const bool skip_gemm = (p.debug & 1) != 0;
+  const bool helper_prefetch = static_cast<uint32_t>(nX) * xstage <= 8u * 8192u;   // (see helper_attention)
 
   if (warp == 0) {
     // ------------------------------------------------------------------ W producer
@@ -811,14 +817,14 @@ __global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const __grid_c
     ComputeCtx hc;
     init_attn_ctx(p, hc, 8, lane, cta, tbl, gen + nW * kWStage, x_ring, strips);
     if (skip_gemm) {
-      for (int l = 0; l < p.L; ++l) helper_attention(p, hc, cta, l, vgo, vdone);
+      for (int l = 0; l < p.L; ++l) helper_attention(p, hc, cta, l, vgo, vdone, helper_prefetch);
     } else {
       uint32_t s = 0, ph = 0;
 #pragma unroll 1
       for (int l = 0; l < p.L; ++l) {
 #pragma unroll 1
         for (int kind = 0; kind < 4; ++kind) {
-          if (kind == 1) helper_attention(p, hc, cta, l, vgo, vdone);   // between the c_attn and the c_proj tiles
+          if (kind == 1) helper_attention(p, hc, cta, l, vgo, vdone, helper_prefetch);   // between the c_attn and the c_proj tiles
           const CUtensorMap* xm = (kind == 1) ? &xmap_att : (kind == 3) ? &xmap_mlp : &xmap_x;
           const KindSched sc = sched[kind];
           if (sc.n == 0) continue;
@@ -858,7 +864,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const __grid_c
     ComputeCtx hc;
     init_attn_ctx(p, hc, 9, lane, cta, tbl, gen + nW * kWStage, x_ring, strips);
     if (skip_gemm) {
-      for (int l = 0; l < p.L; ++l) helper_attention(p, hc, cta, l, vgo, vdone);
+      for (int l = 0; l < p.L; ++l) helper_attention(p, hc, cta, l, vgo, vdone, helper_prefetch);
     } else {
       // The issue loop is instruction bound (one warp, dependent address arithmetic in front of every tcgen05.mma), so
       // it works on slot PAIRS: one set of waits, one descriptor computation (kept incrementally, no multiplies) and
@@ -874,7 +880,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const __grid_c
       for (int l = 0; l < p.L; ++l) {
 #pragma unroll 1
         for (int kind = 0; kind < 4; ++kind) {
-          if (kind == 1) helper_attention(p, hc, cta, l, vgo, vdone);   // all c_attn MMAs of this CTA are issued
+          if (kind == 1) helper_attention(p, hc, cta, l, vgo, vdone, helper_prefetch);   // all c_attn MMAs of this CTA are issued
           const KindSched sc = sched[kind];
           int kb = sc.kb0;          // k block of the next unit inside its row tile
           int seg_left = 0;         // units left in the current segment (0: the next unit opens one)
@@ -946,7 +952,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const __grid_c
     // ------------------------------------------------------------------ TMEM owner: attention helper only
     ComputeCtx hc;
     init_attn_ctx(p, hc, 10, lane, cta, tbl, gen + nW * kWStage, x_ring, strips);
-    for (int l = 0; l < p.L; ++l) helper_attention(p, hc, cta, l, vgo, vdone);
+    for (int l = 0; l < p.L; ++l) helper_attention(p, hc, cta, l, vgo, vdone, helper_prefetch);
   } else if (warp >= kComputeWarp0) {
     // ------------------------------------------------------------------ compute warps
     ComputeCtx cc;
