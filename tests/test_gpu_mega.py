@@ -142,6 +142,32 @@ def test_gpt2_xl_shaped_layers_match_operator_chain():
     eng.close()
 
 
+@pytest.mark.parametrize("rows", [16, 33, 100, 128, 129, 160, 176, 208, 255, 256])
+def test_row_counts_across_the_ring_configurations(rows):
+    """GPT2-XL-shaped layers at row counts that switch the kernel's shared-memory plan: X ring of 8 / 4 / 3 tiles, slot
+    pairs vs single slots (> 128 rows), helper-warp staging behind vs inside the ring (> ~170 rows).  Activations after one
+    decode step against the operator chain, twice (the second pass must reproduce the first bit for bit)."""
+    import clipcap_b200 as cc
+    from clipcap_b200 import synthetic
+    cfg = cc.EngineConfig(lm_layers=3, map_kind="none", vit=False, max_images=256, max_beam=1, max_ctx=64, lm_vocab=2048)
+    eng = cc.Engine(cfg)
+    eng.load_state_dict(synthetic.lm_state_dict(cfg, 1234, "cuda"), prefix="language_model.")
+    eng.check_weights()
+    torch.manual_seed(rows)
+    embeds = (0.5 * torch.randn(rows, 21, cfg.lm_d, device="cuda")).contiguous()
+    p1 = eng.gen_params("greedy", 2, stop_token=-1, max_stops=0)
+    buf = {}
+    for tag, on in (("mega", True), ("chain", False), ("mega2", True)):
+        assert set_mega(eng, on) == 1
+        eng.generate(embeds, p1)
+        torch.cuda.synchronize()
+        buf[tag] = (grab(eng, 1, rows * cfg.lm_d, torch.bfloat16), grab(eng, 0, rows * cfg.lm_d, torch.float32))
+    for k in range(2):
+        assert (buf["mega"][k] - buf["chain"][k]).abs().max().item() <= TOL * buf["chain"][k].abs().max().item(), (rows, k)
+        assert torch.equal(buf["mega"][k], buf["mega2"][k]), (rows, k)
+    eng.close()
+
+
 def test_gptj_is_served_by_the_operator_chain():
     import clipcap_b200 as cc
     fx = torch.load(os.path.join(GOLDEN, "tiny_gptj.pt"), weights_only=False)
