@@ -149,3 +149,23 @@ def test_clip_text_tower_at_full_size():
     assert feats.shape == ref.shape == (B, 512)
     assert rel(feats, ref) <= TOL
     eng.close()
+
+
+def test_all_vit_features_path_at_full_size():
+    """use_all_vit_features at ViT-B/32 + d = 1600 sizes: 50 projected ViT tokens per image and the
+    TransformerMapperAllFeatures mapper (S = 90) against the fp32 oracle on the GPU."""
+    import clipcap_b200 as cc
+    from clipcap_b200 import synthetic
+    cfg = cc.EngineConfig(lm_layers=1, lm_vocab=2048, map_kind="transformer_all", map_clip_len=50, max_images=8, max_ctx=64)
+    eng = cc.Engine(cfg)
+    sds = synthetic.load_synthetic(eng)
+    images = synthetic.synthetic_images(8, cfg, device="cuda")
+    toks = eng.vit_encode(images)
+    ref_toks = orc.vit_forward(sds["vit"], images, cfg.vit_heads, cfg.vit_patch, all_tokens=True)
+    assert toks.shape == ref_toks.shape == (8, 50, 512)
+    assert rel(toks, ref_toks) <= TOL
+    prefix = eng.map_prefix(ref_toks)
+    ref_prefix = orc.mapper_all_forward(sds["mapper"], ref_toks, cfg.map_heads, "relu")
+    assert prefix.shape == ref_prefix.shape == (8, 40, 1600)
+    assert rel(prefix, ref_prefix) <= TOL
+    eng.close()
