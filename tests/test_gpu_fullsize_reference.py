@@ -169,3 +169,46 @@ def test_all_vit_features_path_at_full_size():
     assert prefix.shape == ref_prefix.shape == (8, 40, 1600)
     assert rel(prefix, ref_prefix) <= TOL
     eng.close()
+
+
+def test_gptj_6b_against_transformers_fp32():
+    """Config 5's language model (GPT-J-6B shapes: d = 4096, 28 layers, 16 heads of 256, rotary 64, untied biased head)
+    against `transformers.GPTJForCausalLM` in fp32 -- the class lms/GPTJ.py:5 instantiates -- on the same bf16-rounded
+    weights: teacher-forced logits within 2e-2, greedy tokens of the KV-cached decode equal to the reference's argmax."""
+    transformers = pytest.importorskip("transformers")
+    import clipcap_b200 as cc
+    from clipcap_b200 import synthetic
+    cfg = cc.EngineConfig(lm_arch="gptj", lm_d=4096, lm_layers=28, lm_heads=16, lm_vocab=50400, lm_n_pos=2048, lm_rotary_dim=64,
+                          map_kind="none", vit=False, max_images=8, max_ctx=48)
+    eng = cc.Engine(cfg)
+    sd = synthetic.lm_state_dict(cfg, 1234, "cuda")
+    eng.load_state_dict(sd, prefix="language_model.")
+    eng.check_weights()
+    hf_cfg = transformers.GPTJConfig(vocab_size=cfg.lm_vocab, n_positions=cfg.lm_n_pos, n_embd=cfg.lm_d, n_layer=cfg.lm_layers,
+                                     n_head=cfg.lm_heads, rotary_dim=cfg.lm_rotary_dim)
+    with torch.device("cuda"):
+        hf = transformers.GPTJForCausalLM(hf_cfg)
+    res = hf.load_state_dict(sd, strict=False)
+    assert not res.unexpected_keys
+    assert all(("attn.bias" in k) or ("masked_bias" in k) or ("embed_positions" in k) for k in res.missing_keys), res.missing_keys
+    hf = hf.float().eval()
+    N, P, T = 8, 12, 8
+    torch.manual_seed(5)
+    prefix = (0.05 * torch.randn(N, P, cfg.lm_d, device="cuda")).contiguous()
+    p = eng.gen_params("greedy", T, stop_token=-1, max_stops=0)
+    tokens, _, _ = eng.generate(prefix, p)
+    torch.cuda.synchronize()
+    tokens = tokens.long()
+    emb = torch.cat([prefix, eng.embed_tokens(tokens[:, :T - 1])], dim=1)
+    with torch.no_grad():
+        ref_logits = hf(inputs_embeds=emb).logits.float()
+    ours = eng.lm_forward(emb)
+    assert rel(ours, ref_logits) <= TOL
+    pred = ref_logits[:, P - 1:P - 1 + T]
+    agree = pred.argmax(-1) == tokens
+    scale = (pred.max() - pred.min()).item()
+    for r, t in (~agree).nonzero().tolist():
+        assert (pred[r, t].max() - pred[r, t, tokens[r, t]]).item() <= TOL * scale, (r, t)
+    assert agree.float().mean().item() >= 0.95
+    print("GPT-J-6B: greedy tokens identical to transformers fp32 at %.1f %% of %d positions" % (100 * agree.float().mean().item(), agree.numel()))
+    eng.close()
