@@ -119,6 +119,8 @@ struct ComputeCtx {
   int u_ctx[4], u_page[4];  // cached tokens / this lane's page id of the warp's first four attention units
   unsigned long long* trace;
   int trace_it;
+  unsigned long long* rtrace;   // (tuning) this CTA's 64 role stamps, or null
+  int cur_layer;
 };
 
 __device__ __forceinline__ float compute_sum(ComputeCtx& cc, float v) {
@@ -146,7 +148,10 @@ __device__ __forceinline__ void grid_arrive(ComputeCtx& cc, uint32_t xgo_bar, ui
   ptx::named_bar_sync(1, kComputeThreads);
   stamp(cc);
   if (cc.ct == 0) {
-    if (helpers_bar != 0) ptx::mbar_wait(helpers_bar, helpers_parity);  // the helper warps' share of the phase is stored
+    if (helpers_bar != 0) {
+      ptx::mbar_wait(helpers_bar, helpers_parity);  // the helper warps' share of the phase is stored
+      if (cc.rtrace != nullptr && cc.cur_layer == 1) cc.rtrace[44] = ptx::globaltimer_ns();
+    }
     fence_proxy_async_all();  // the global writes are read through TMA (async proxy) by other CTAs
     red_release_add(cc.ctr, 1u);
     if (xgo_bar != 0) ptx::mbar_arrive(xgo_bar);  // the X producer may start polling for this barrier
@@ -157,22 +162,6 @@ __device__ __forceinline__ void grid_wait(ComputeCtx& cc, unsigned n) {
   if (cc.ct == 0) poll_counter(cc.ctr, n * cc.ncta);
   ptx::named_bar_sync(1, kComputeThreads);
   stamp(cc);
-}
-
-// sum of the split-K partial slots of 4 consecutive outputs, slots added in slot order; loads issued 8 at a time
-__device__ __forceinline__ float4 sum_slots4(const float* src, uint32_t slot_stride, int nsl) {
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 1
-  for (int s0 = 0; s0 < nsl; s0 += 8) {
-    float4 w[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) w[j] = (s0 + j < nsl) ? ldcg_f4(src + (s0 + j) * slot_stride) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      acc.x += w[j].x; acc.y += w[j].y; acc.z += w[j].z; acc.w += w[j].w;
-    }
-  }
-  return acc;
 }
 
 // h[t] = (embed | h[t] + bias + sum of split-K partials); x[t] = LayerNorm(h[t]) for the rows t = cta, cta + ncta, ...
@@ -288,7 +277,11 @@ __device__ __noinline__ void ln_phase(const MegaParams& p, ComputeCtx& cc, int c
 }
 
 // mlp[t, f] = gelu_new(sum of c_fc partials + bias)
+// A thread owns up to three float4 items (64 rows x 6400 features on 148 x 256 threads = 2.7 per thread).  The phase is
+// a chain of L2 round trips, so the slot loads of ALL its items are issued before the first one is used (one round trip
+// instead of one per item).
 __device__ __noinline__ void gelu_phase(const MegaParams& p, ComputeCtx& cc, int cta, const float* bias) {
+  constexpr int kItems = 3, kSl = 4;
   const uint32_t rows_out = p.g[2].rows_out, tbl_off = p.g[2].tbl_off;
   const uint32_t nq = rows_out >> 2;
   const uint32_t total = static_cast<uint32_t>(p.R) * nq;
@@ -297,24 +290,49 @@ __device__ __noinline__ void gelu_phase(const MegaParams& p, ComputeCtx& cc, int
   const uint32_t* const tbl = cc.tbl;
   const float* const ws = p.ws;
   bf16* const mlp = p.mlp;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
-  for (uint32_t idx = static_cast<uint32_t>(cta) * kComputeThreads + cc.ct; idx < total; idx += step) {
-    const uint32_t t = idx / nq, q = idx - t * nq;
-    const int nsl = static_cast<int>(tbl[tbl_off + (q >> 5)] >> 16);
-    const float4 acc = sum_slots4(ws + (t * rows_out + (q << 2)), slot_stride, nsl);
-    const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + q);
-    float o[4] = {acc.x + b.x, acc.y + b.y, acc.z + b.z, acc.w + b.w};
+  for (uint32_t idx0 = static_cast<uint32_t>(cta) * kComputeThreads + cc.ct; idx0 < total; idx0 += kItems * step) {
+    float4 w[kItems][kSl], b[kItems];
+    uint32_t off[kItems], q[kItems];
+    int nsl[kItems];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      // same form as the GEMM epilogue's gelu_new: 0.5 x (1 + tanh(u)) == x - x / (1 + exp(2u))
-      const float xx = o[k];
-      const float u = 0.7978845608028654f * (xx + 0.044715f * xx * xx * xx);
-      o[k] = xx - __fdividef(xx, 1.f + __expf(2.f * u));
+    for (int j = 0; j < kItems; ++j) {
+      const uint32_t idx = idx0 + j * step;
+      const bool ok = idx < total;
+      const uint32_t t = ok ? idx / nq : 0u;
+      q[j] = ok ? idx - t * nq : 0u;
+      off[j] = t * rows_out + (q[j] << 2);
+      nsl[j] = ok ? static_cast<int>(tbl[tbl_off + (q[j] >> 5)] >> 16) : -1;
+#pragma unroll
+      for (int sl = 0; sl < kSl; ++sl) w[j][sl] = (sl < nsl[j]) ? ldcg_f4(ws + off[j] + sl * slot_stride) : z4;
+      b[j] = __ldg(reinterpret_cast<const float4*>(bias) + q[j]);
     }
-    uint2 pk;
-    pk.x = pack_bf16x2(o[0], o[1]);
-    pk.y = pack_bf16x2(o[2], o[3]);
-    *(reinterpret_cast<uint2*>(mlp + t * rows_out) + q) = pk;
+#pragma unroll
+    for (int j = 0; j < kItems; ++j) {
+      if (nsl[j] < 0) continue;
+      float4 acc = z4;
+#pragma unroll
+      for (int sl = 0; sl < kSl; ++sl) {   // slot order (absent slots add zero)
+        acc.x += w[j][sl].x; acc.y += w[j][sl].y; acc.z += w[j][sl].z; acc.w += w[j][sl].w;
+      }
+      for (int sl = kSl; sl < nsl[j]; ++sl) {  // (more than four contributors per tile: small K only)
+        const float4 e = ldcg_f4(ws + off[j] + sl * slot_stride);
+        acc.x += e.x; acc.y += e.y; acc.z += e.z; acc.w += e.w;
+      }
+      float o[4] = {acc.x + b[j].x, acc.y + b[j].y, acc.z + b[j].z, acc.w + b[j].w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        // same form as the GEMM epilogue's gelu_new: 0.5 x (1 + tanh(u)) == x - x / (1 + exp(2u))
+        const float xx = o[k];
+        const float u = 0.7978845608028654f * (xx + 0.044715f * xx * xx * xx);
+        o[k] = xx - __fdividef(xx, 1.f + __expf(2.f * u));
+      }
+      uint2 pk;
+      pk.x = pack_bf16x2(o[0], o[1]);
+      pk.y = pack_bf16x2(o[2], o[3]);
+      *reinterpret_cast<uint2*>(mlp + off[j]) = pk;
+    }
   }
 }
 
@@ -585,6 +603,8 @@ __device__ __forceinline__ void init_attn_ctx(const MegaParams& p, ComputeCtx& c
   cc.strips = strips;
   cc.attn_prefetched = false;
   cc.a_k = cc.a_ib = cc.a_h = cc.a_inflight = 0;
+  cc.rtrace = p.trace ? p.trace + static_cast<size_t>(p.ncta) * (2 * (8 * p.L + 2)) + static_cast<size_t>(cta) * 64 : nullptr;
+  cc.cur_layer = 0;
 #pragma unroll
   for (int ui = 0; ui < 4; ++ui) {
     const int unit = (aw + kAttnWarps * ui) * p.ncta + cta;
@@ -611,10 +631,15 @@ __device__ __forceinline__ void helper_attention(const MegaParams& p, ComputeCtx
   // (seen as run-to-run differences of sampled / beam captions at >= 200 rows): then the copies start after vgo.
   if (early_prefetch) attention_phase(p, hc, cta, l, bias, true);
   ptx::mbar_wait(vgo, static_cast<uint32_t>(l) & 1u);
+  if (hc.lane == 0 && hc.cw == 8) MEGA_RSTAMP(l, 48);
   attention_phase(p, hc, cta, l, bias, false);
   fence_proxy_async_all();   // att rows are fetched by other CTAs through TMA
   __syncwarp();
-  if (hc.lane == 0) ptx::mbar_arrive(vdone);
+  if (hc.lane == 0) {
+    MEGA_RSTAMP(l, 45 + hc.cw - 8);
+    ptx::mbar_arrive(vdone);
+  }
+
 }
 
 struct EpiCtx {
@@ -980,6 +1005,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const __grid_c
 #pragma unroll 1
     for (int l = 0; l < p.L; ++l) {
       const MegaLayer ly = p.layers[l];
+      cc.cur_layer = l;
       if (l > 0) grid_wait(cc, 8 * l);
       ln_phase(p, cc, cta, l == 0, 3, l > 0 ? p.layers[l - 1].b_fc2 : nullptr, ly.ln1_g, ly.ln1_b);
       grid_arrive(cc, xgo);     // #8l
@@ -991,6 +1017,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const __grid_c
       grid_wait(cc, 8 * l + 2);
       if (cc.ct == 0) ptx::mbar_arrive(vgo);   // the helper warps start their units
       attention_phase(p, cc, cta, l, ly.b_qkv, false);
+      if (lane == 0) MEGA_RSTAMP(l, 50 + cc.cw);
       grid_arrive(cc, xgo, vdone, static_cast<uint32_t>(l) & 1u);     // #8l+2
       epilogue_phase(p, cc, ec, cta, 1, l);
       if (sched[1].n == 0) grid_wait(cc, 8 * l + 3);  // (see grid_arrive: no arrival at #k+1 before #k is complete)

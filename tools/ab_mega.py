@@ -51,6 +51,11 @@ if want_trace:
     names_a = ["enter", "qkv folded", "new token", "b0 read", "b0 issued", "b1 read", "b1 issued", "b2 read", "b2 issued", "b3 read", "b3 issued", "batches done"]
     for c in (0, 70, 147):
         print("  CTA %3d attention unit of compute warp 1 (us after attn.wait): " % c + "  ".join("%s %.2f" % (names_a[k], (float(r[c, 32 + k]) - float(t[c, 11 + 2])) / 1e3) for k in range(12) if r[c, 32 + k] > 0))
+    for c in (0, 70, 147):
+        b0 = float(t[c, 11 + 3])
+        f = lambda k: "%.2f" % ((float(r[c, k]) - b0) / 1e3) if r[c, k] > 0 else "-"
+        print("  CTA %3d (us after its attn.wait): helper go %s, helpers done %s %s %s, compute warps done %s, thread 0 past helpers %s" % (
+            c, f(48), f(45), f(46), f(47), " ".join(f(50 + w) for w in range(8)), f(44)))
     for c in ():
         print("  CTA %3d fc units: x issue  " % c + " ".join("%6.2f" % ((float(v) - base1) / 1e3) if v > 0 else "   -  " for v in r[c, 44:54]))
         print("                   w ready  " + " ".join("%6.2f" % ((float(v) - base1) / 1e3) if v > 0 else "   -  " for v in r[c, 54:64]))
