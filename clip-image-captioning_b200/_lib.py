@@ -61,6 +61,7 @@ PROTOTYPES = {
     "ccb_timing_sum": (_I, [_P, _I, C.POINTER(_F), C.POINTER(_F), C.POINTER(_I)]),
     "ccb_sample": (_I, [_P, _P, _L, _I, _I, C.POINTER(GenParams), _P, _L, _I, _I, _P, _P, _P, _P]),
     "ccb_argmax": (_I, [_P, _P, _L, _I, _I, _P, _P]),
+    "ccb_cross_entropy": (_I, [_P, _P, _L, _I, _I, _P, _P, _I, _P, _P, _P]),
     "ccb_beam_step": (_I, [_P, _P, _L, _I, _I, _I, _F, _I, _I, _P, _P, _P, _P, _I, _P, _P, _P]),
     "ccb_op_linear": (_I, [_P, _P, _L, _I, _P, _I, _I, _P, _I, _P, _L, _P, _L, _I, _I, _I, _I, _P]),
     "ccb_debug_gemm_trace": (_I, [_P, _P, _L, _I]),

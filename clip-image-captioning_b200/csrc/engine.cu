@@ -1222,6 +1222,15 @@ int ccb_argmax(ccb_ctx* c, const float* logits, int64_t ld, int B, int V, int32_
   return 0;
 }
 
+int ccb_cross_entropy(ccb_ctx* c, const float* logits, int64_t ld, int rows, int V, const int32_t* targets,
+                      const int32_t* row_map, int ignore_index, float* row_loss, float* loss_out, void* stream) {
+  if (!c || !logits || !targets || !row_loss || !loss_out) return fail(c, "ccb_cross_entropy: null argument");
+  if (rows <= 0 || V <= 0 || ld < V) return fail(c, "ccb_cross_entropy: rows=%d V=%d ld=%lld", rows, V, static_cast<long long>(ld));
+  RUN(cross_entropy(logits, ld, rows, V, targets, row_map, ignore_index, row_loss, loss_out, static_cast<cudaStream_t>(stream)));
+  c->launches++;   // (two kernels)
+  return 0;
+}
+
 int ccb_beam_step(ccb_ctx* c, const float* logits, int64_t ld, int N, int beam, int V, float temperature,
                   int stop_token, int step, float* scores, float* seq_lengths, uint8_t* has_stopped, int32_t* tokens,
                   int max_len, int32_t* next_tokens, int32_t* src_rows, void* stream) {

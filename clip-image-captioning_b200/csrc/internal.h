@@ -140,6 +140,9 @@ struct SamplerScratch {
 };
 // greedy: next[b] = argmax_v logits[b, v] (lowest index wins ties)
 int sample_greedy(const float* logits, long long ld, int B, int V, int* next, cudaStream_t s);
+// mean cross entropy over the rows whose target != ignore_index; row_loss [rows], out2 = {mean, counted rows}
+int cross_entropy(const float* logits, long long ld, int rows, int V, const int* targets, const int* row_map, int ignore_index,
+                  float* row_loss, float* out2, cudaStream_t s);
 // nucleus / top-k sampling following sampling.py:114-162 + multinomial (== argmax(p / q), q ~ Exp(1)):
 //   logits <- repetition penalty over history (optional) -> / temperature -> top-k -> top-p -> typical-p -> softmax -> sample
 // top_p / top_k may be per-row device arrays (or null -> scalar). q_noise [B, ldq] f32 Exp(1) samples or null

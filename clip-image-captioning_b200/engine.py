@@ -410,6 +410,29 @@ class Engine:
         self._check(self.lib.ccb_argmax(self._h, _ptr(logits), logits.stride(0), B, V, _ptr(nxt), self._stream()))
         return nxt
 
+    def cross_entropy(self, logits: torch.Tensor, targets: torch.Tensor, ignore_index: int = -100,
+                      row_map: Optional[torch.Tensor] = None):
+        """`F.cross_entropy(logits, targets, ignore_index=...)` (mean reduction) on the device: logits [n, V] f32 (rows may be
+        strided), targets [rows]; `row_map` [rows] picks the logits row of each target (default: row r).  Returns
+        (loss 0-d tensor, per-row loss [rows], number of counted rows 0-d tensor)."""
+        if logits.dim() != 2 or logits.stride(1) != 1:
+            raise ValueError("cross_entropy: logits must be [n, V] with unit stride along V")
+        logits = self._dev(logits, torch.float32)
+        tg = self._dev(targets).to(torch.int32).contiguous().view(-1)
+        rows, V = tg.numel(), logits.shape[1]
+        rm = None
+        if row_map is not None:
+            rm = self._dev(row_map).to(torch.int32).contiguous().view(-1)
+            if rm.numel() != rows:
+                raise ValueError("cross_entropy: row_map and targets differ in length")
+        elif logits.shape[0] != rows:
+            raise ValueError("cross_entropy: %d logits rows for %d targets" % (logits.shape[0], rows))
+        row_loss = torch.empty(rows, device=self.device, dtype=torch.float32)
+        out = torch.empty(2, device=self.device, dtype=torch.float32)
+        self._check(self.lib.ccb_cross_entropy(self._h, _ptr(logits), logits.stride(0), rows, V, _ptr(tg), _ptr(rm), ignore_index,
+                                               _ptr(row_loss), _ptr(out), self._stream()))
+        return out[0], row_loss, out[1]
+
     def beam_step(self, logits, scores, seq_lengths, has_stopped, tokens, step: int, beam: int, temperature=1.0,
                   stop_token=13):
         """One step of inference.py:98-131 for N images; state tensors are updated in place."""

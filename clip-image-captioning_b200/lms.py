@@ -9,7 +9,6 @@ from types import SimpleNamespace
 from typing import Optional
 
 import torch
-import torch.nn.functional as F
 
 from .engine import Engine
 
@@ -38,10 +37,12 @@ class _EngineLM:
             raise ValueError("inputs_embeds is required (the reference never calls the LM with input_ids)")
         logits = self.engine.lm_forward(inputs_embeds, attention_mask)
         loss = None
-        if labels is not None:  # HF causal-LM loss: shift by one, ignore_index -100
-            lg = logits[:, :-1, :].float()
-            lb = labels.to(logits.device)[:, 1:]
-            loss = F.cross_entropy(lg.reshape(-1, lg.shape[-1]), lb.reshape(-1), ignore_index=-100)
+        if labels is not None:  # HF causal-LM loss: position t predicts label t + 1, ignore_index -100, mean
+            B, S, V = logits.shape
+            dev = logits.device
+            flat = logits.as_strided((B * S, V), (logits.stride(1), 1), logits.storage_offset())
+            row_map = (torch.arange(B, device=dev)[:, None] * S + torch.arange(S - 1, device=dev)[None, :]).reshape(-1)
+            loss, _, _ = self.engine.cross_entropy(flat, labels.to(dev)[:, 1:].reshape(-1), ignore_index=-100, row_map=row_map)
         return SimpleNamespace(logits=logits, loss=loss)
 
     __call__ = call

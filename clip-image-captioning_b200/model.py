@@ -88,6 +88,24 @@ class CLIPCaptionModel:
 
     __call__ = forward
 
+    def caption_loss(self, tokens: torch.Tensor, prefix: torch.Tensor, mask: Optional[torch.Tensor] = None,
+                     ignore_index: int = 0) -> torch.Tensor:
+        """The teacher-forced loss of evaluate_model.py:497-516 (validation) and model.py:204-211 (training_step), forward
+        only: `cross_entropy(forward(tokens, prefix, mask).logits[:, P-1:-1].reshape(-1, V), tokens.flatten(),
+        ignore_index=0)`.  The logits slice is addressed through a row map instead of being copied."""
+        tokens = tokens.to(self.device)
+        if mask is None:
+            mask = tokens.ge(0)                      # model.py:204-205
+            tokens = tokens.masked_fill(~mask, 0)
+        out = self.forward(tokens, prefix, mask)
+        logits = out.logits                          # [B, P + L, V] view of a [B * (P + L), ldv] buffer
+        B, S, V = logits.shape
+        L, P = tokens.shape[1], self.prefix_length
+        flat = logits.as_strided((B * S, V), (logits.stride(1), 1), logits.storage_offset())
+        row_map = (torch.arange(B, device=self.device)[:, None] * S + (P - 1) + torch.arange(L, device=self.device)[None, :])
+        loss, _, _ = self.engine.cross_entropy(flat, tokens.reshape(-1), ignore_index=ignore_index, row_map=row_map.reshape(-1))
+        return loss
+
 
 class CLIPCaptionPrefixOnly(CLIPCaptionModel):  # model.py:219-225 (training-time distinction only)
     pass

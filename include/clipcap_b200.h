@@ -169,6 +169,13 @@ CCB_API int ccb_sample(ccb_ctx* ctx, const float* logits, int64_t ld, int B, int
                int32_t* next_out, int32_t* alt_out, void* stream);
 /* argmax with lowest-index tie rule (generate_beam with beam_size=1) */
 CCB_API int ccb_argmax(ccb_ctx* ctx, const float* logits, int64_t ld, int B, int V, int32_t* next_out, void* stream);
+/* teacher-forced loss: F.cross_entropy(logits.reshape(-1, V), tokens.flatten(), ignore_index=0) of
+ * evaluate_model.py:511-514 (validation) and model.py:210-211 (training_step), forward only.  logits [*, ld] f32;
+ * targets [rows] int32; row_map optional [rows] int32 = logits row of each target (the reference's
+ * `logits[:, prefix_length-1:-1]` slice without a copy; NULL = row r); row_loss [rows] f32 out (0 for ignored rows);
+ * loss_out [2] f32 = {mean over the rows with target != ignore_index (NaN if none), number of such rows}. */
+CCB_API int ccb_cross_entropy(ccb_ctx* ctx, const float* logits, int64_t ld, int rows, int V, const int32_t* targets,
+               const int32_t* row_map, int ignore_index, float* row_loss, float* loss_out, void* stream);
 /* one beam-search step on caller state (inference.py:98-131): logits [N*beam, ld] (step 0: [N, ld]);
  * scores/seq_lengths [N,beam] f32, has_stopped [N,beam] uint8, tokens [N,beam,max_len] int32 updated in place;
  * next_tokens / src_rows [N*beam] int32 out. */

@@ -294,6 +294,20 @@ def caption_model_forward(lm: OracleLM, mapper_fn, tokens, prefix, mask):
     return lm.logits(emb, full_mask)
 
 
+def caption_loss(lm: OracleLM, mapper_fn, tokens, prefix, mask, prefix_length: int, ignore_index: int = 0):
+    """The teacher-forced loss of model.py:204-211 (training_step) and evaluate_model.py:505-514 (validation):
+    positions outside `mask` become token 0, the logits of positions P-1 .. P+L-2 predict tokens 0 .. L-1, mean negative
+    log-likelihood over the targets that are not `ignore_index` (0: padding AND any genuine token 0, as in the reference).
+    Written out (log-softmax by hand) rather than through F.cross_entropy, which is what the reference calls."""
+    tokens = tokens.clone()
+    tokens[~mask.bool()] = 0
+    logits = caption_model_forward(lm, mapper_fn, tokens, prefix, mask)[:, prefix_length - 1: -1].double()
+    lse = torch.logsumexp(logits, dim=-1)
+    nll = lse - logits.gather(-1, tokens[..., None]).squeeze(-1)
+    keep = tokens != ignore_index
+    return (nll * keep).sum() / keep.sum(), (nll * keep).float()
+
+
 # ------------------------------------------------------------------------------------------------ logit processors
 # Tie rule.  The reference sorts with torch.sort(descending=True), whose order among EQUAL logits is unspecified
 # (it differs between the CPU and CUDA back ends).  Which of several logits tied exactly at the nucleus boundary

@@ -125,3 +125,45 @@ def test_argmax_lowest_index_on_ties(tiny_engine):
     ref = logits.argmax(-1)
     ref[3] = 100
     assert nxt.cpu().tolist() == ref.tolist()
+
+
+def test_argmax_strided_and_unaligned_rows(tiny_engine):
+    """Rows that start on a 16-byte boundary take the float4 path, others the scalar one; ties inside one float4 and the
+    scalar tail (V % 4) follow the same lowest-index rule."""
+    g = torch.Generator().manual_seed(1)
+    for V, ld in ((50257, 50257), (50257, 50264), (50400, 50400), (1027, 1031)):
+        buf = torch.randn(9, ld, generator=g).cuda()
+        logits = buf[:, :V]
+        logits[2, 5] = logits[2, 6] = 50.0          # tie inside one float4
+        logits[4, V - 1] = 60.0                     # scalar tail
+        logits[6, 17] = logits[6, V - 2] = 70.0
+        nxt = tiny_engine.argmax(logits)
+        ref = logits.argmax(-1)
+        ref[2], ref[4], ref[6] = 5, V - 1, 17
+        assert nxt.cpu().tolist() == ref.cpu().tolist()
+
+
+def test_cross_entropy_at_full_vocabulary(tiny_engine):
+    """ccb_cross_entropy against torch's F.cross_entropy (what the reference calls, model.py:210) at V = 50257 on 64 x 20
+    target rows: mean within 1e-5 relative, per-row within 1e-4 absolute; ignored rows, a row map, all rows ignored (NaN)."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(2)
+    V, rows = 50257, 1280
+    logits = (3.0 * torch.randn(rows + 64, V, generator=g)).cuda()
+    targets = torch.randint(0, V, (rows,), generator=g).cuda()
+    targets[::7] = 0
+    row_map = torch.randperm(rows + 64, generator=g)[:rows].cuda()
+    loss, row_loss, n = tiny_engine.cross_entropy(logits, targets, ignore_index=0, row_map=row_map)
+    picked = logits[row_map]
+    want = F.cross_entropy(picked, targets, ignore_index=0)
+    want_rows = F.cross_entropy(picked, targets, ignore_index=0, reduction="none")
+    assert abs(float(loss) - float(want)) <= 1e-5 * abs(float(want))
+    assert (row_loss - want_rows).abs().max().item() <= 1e-4
+    assert int(n) == int((targets != 0).sum())
+    loss2, _, _ = tiny_engine.cross_entropy(logits[:rows], targets, ignore_index=0)
+    assert abs(float(loss2) - float(F.cross_entropy(logits[:rows], targets, ignore_index=0))) <= 1e-5 * abs(float(want))
+    loss3, _, n3 = tiny_engine.cross_entropy(logits[:4], torch.zeros(4, dtype=torch.int64), ignore_index=0)
+    assert torch.isnan(loss3).item() and int(n3) == 0
+    # bit-identical run to run (row-order sum by one CTA)
+    again, _, _ = tiny_engine.cross_entropy(logits, targets, ignore_index=0, row_map=row_map)
+    assert float(again) == float(loss)

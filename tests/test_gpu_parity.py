@@ -75,6 +75,42 @@ def test_teacher_forced_forward_with_mask(setup):
     assert rel_err(logits, fx["logits_tf"]) <= TOL
 
 
+def test_caption_loss(setup):
+    """model.py:204-211 / evaluate_model.py:505-514 through CLIPCaptionModel.caption_loss -> ccb_cross_entropy: within 2e-2 of
+    the reference value (bf16 logits), and the CE kernel itself within 1e-5 of torch on the same logits."""
+    import clipcap_b200 as cc
+    eng, fx = setup
+    want = torch.load(os.path.join(GOLDEN, "tiny_loss.pt"), weights_only=False)[fx["arch"]]
+    model = cc.model.CLIPCaptionModel(eng)
+    tokens = fx["tokens"].clone()
+    tokens[~fx["mask"]] = -1                       # the dataset's padding (model.py:204: mask = tokens.ge(0))
+    loss = model.caption_loss(tokens, fx["feat"])
+    assert abs(float(loss) - float(want["loss"])) <= TOL * abs(float(want["loss"]))
+    loss2 = model.caption_loss(want["tokens"], fx["feat"], fx["mask"])
+    assert float(loss2) == float(loss)
+    # the kernel on the reference's own logits
+    P = fx["P"]
+    lg = fx["logits_tf"][:, P - 1:-1].reshape(-1, fx["V"]).cuda()
+    l3, rows, n = eng.cross_entropy(lg, want["tokens"].reshape(-1), ignore_index=0)
+    assert abs(float(l3) - float(want["loss"])) <= 1e-5 * abs(float(want["loss"]))
+    assert (rows.cpu() - want["row_loss"]).abs().max().item() <= 1e-4
+    assert int(n) == int((want["tokens"] != 0).sum())
+
+
+def test_lm_call_with_labels_returns_hf_loss(setup):
+    """lms/GPT2.py:17-19 with labels: HF's shifted causal-LM loss (ignore_index -100) on the device."""
+    import torch.nn.functional as F
+    import clipcap_b200 as cc
+    eng, fx = setup
+    lm = cc.model.CLIPCaptionModel(eng).language_model
+    labels = torch.randint(0, fx["V"], fx["prefix"].shape[:2])
+    labels[:, :2] = -100
+    out = lm.call(inputs_embeds=fx["prefix"], labels=labels)
+    lg = out.logits[:, :-1].float().reshape(-1, fx["V"])
+    want = F.cross_entropy(lg, labels[:, 1:].reshape(-1).to(lg.device), ignore_index=-100)
+    assert abs(float(out.loss) - float(want)) <= 1e-5 * abs(float(want))
+
+
 def test_embedding_lookup_is_exact(setup):
     eng, fx = setup
     got = eng.embed_tokens(fx["tokens"]).cpu()

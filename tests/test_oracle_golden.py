@@ -62,6 +62,16 @@ def test_caption_model_forward_matches_reference(fx):
     assert close(logits, fx["logits_tf"], 5e-5)
 
 
+def test_caption_loss_matches_reference(fx):
+    """model.py:204-211 / evaluate_model.py:505-514: tiny_loss.pt holds the reference's expression on the reference's logits."""
+    want = load("tiny_loss.pt")[fx["arch"]]
+    mapper = lambda feat: orc.mapper_forward(fx["sd_mapper32"], feat, fx["CL"], fx["map_heads"])
+    loss, rows = orc.caption_loss(fx["lm"], mapper, fx["tokens"], fx["feat"], fx["mask"], fx["P"])
+    assert abs(float(loss) - float(want["loss"])) <= 1e-5 * abs(float(want["loss"]))
+    assert close(rows.reshape(-1), want["row_loss"], 5e-5)
+    assert int((want["tokens"] == 0).sum()) >= 6        # the fixture exercises ignore_index
+
+
 @pytest.mark.parametrize("use_cache", [False, True])
 @pytest.mark.parametrize("key,beam,T,temp", [("greedy", 1, 10, 1.0), ("beam5", 5, 10, 1.0), ("beam3_T2", 3, 8, 2.0)])
 def test_generate_beam_matches_reference(fx, key, beam, T, temp, use_cache):

@@ -389,9 +389,32 @@ def make_generate_fixture(ref, seed):
     return fx
 
 
+def make_loss_fixture():
+    """The teacher-forced loss of model.py:204-211 (training_step) == evaluate_model.py:505-514 (validation), evaluated
+    with the reference's own expression on the logits the unmodified reference model produced for the committed model
+    fixtures (tiny_gpt2.pt / tiny_gptj.pt: `logits_tf = model(tokens, feat, mask).logits`)."""
+    import torch.nn.functional as nnf
+    out = {}
+    for arch in ("gpt2", "gptj"):
+        fx = torch.load(os.path.join(OUT, "tiny_%s.pt" % arch), weights_only=False)
+        tokens, mask, P = fx["tokens"].clone(), fx["mask"], fx["P"]
+        tokens[~mask] = 0                                                   # model.py:205
+        logits = fx["logits_tf"][:, P - 1: -1]                              # model.py:209
+        loss = nnf.cross_entropy(logits.reshape(-1, logits.shape[-1]), tokens.flatten(), ignore_index=0)  # model.py:210
+        rows = nnf.cross_entropy(logits.reshape(-1, logits.shape[-1]), tokens.flatten(), ignore_index=0, reduction="none")
+        out[arch] = {"loss": loss, "row_loss": rows, "tokens": tokens}
+    return out
+
+
 def main():
     ref = ref_harness.load_reference()
     os.makedirs(OUT, exist_ok=True)
+    if "--loss" in sys.argv:
+        fx = make_loss_fixture()
+        path = os.path.join(OUT, "tiny_loss.pt")
+        torch.save(fx, path)
+        print(path, os.path.getsize(path), "B", {k: float(v["loss"]) for k, v in fx.items()})
+        return
     for arch, seed in (() if "--only-typical" in sys.argv else (("gpt2", 11), ("gptj", 12))):
         fx = make_model_fixture(ref, arch, seed)
         path = os.path.join(OUT, "tiny_%s.pt" % arch)
