@@ -483,6 +483,169 @@ __global__ void __launch_bounds__(kDecodeWarps * 32) attention_decode_kernel(
   }
 }
 
+// ------------------------------------------------------------------------------------------------ decode, one CTA per unit
+// attention_decode_kernel gives a (row, head) unit to ONE warp with lane = token: at head_dim 256 (GPT-J) a lane holds a
+// whole 512-byte K row in registers and walks V in four 64-dim chunks, i.e. ~10 dependent HBM round trips per unit, on a
+// grid of rows x heads / 4 CTAs (64 CTAs for 16 rows): 31 us per layer against 2 us of K/V traffic.  Here a unit gets a
+// whole CTA of 128 threads and ALL its K and V rows are requested at once with cp.async (16-byte chunks, coalesced per
+// row) into shared memory -- one HBM round trip per tile of `tile` tokens -- while q / k_new / v_new (rotary, cache
+// append) are prepared underneath.  Scores: CH = HD / 8 lanes per token (one 16-byte chunk each), reduced by shuffles;
+// softmax over the tile through shared memory; output: thread = 2 dims, walking the tile's V rows in shared memory
+// (conflict-free 4-byte reads).  Tiles are folded with an online softmax; the new token is added last.
+constexpr int kWideThreads = 128;
+
+template <int HD>
+__global__ void __launch_bounds__(kWideThreads) attention_decode_wide_kernel(
+    const bf16* __restrict__ qkv, bf16* __restrict__ out, int rows, int H, float scale, KvCache cache, int layer,
+    const int* __restrict__ block_table, const int* __restrict__ ctx_len, int rotary_dim, int tile) {
+  constexpr int CH = HD / 8;            // 16-byte chunks per K / V row
+  constexpr int TPW = 32 / CH;          // tokens a warp scores per iteration (CH <= 32)
+  constexpr int NW = kWideThreads / 32;
+  extern __shared__ __align__(16) uint8_t wsm[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint8_t* Ks = wsm;                                          // [tile][HD] bf16
+  uint8_t* Vs = wsm + static_cast<size_t>(tile) * HD * 2;     // [tile][HD] bf16
+  float* qs = reinterpret_cast<float*>(Vs + static_cast<size_t>(tile) * HD * 2);   // [HD]
+  float* sc = qs + HD;                                        // [tile]
+  float* red = sc + tile;                                     // [2 * NW]
+  ptx::grid_dep_wait();
+  ptx::grid_dep_launch();
+  const int unit = blockIdx.x;
+  const int b = unit / H, h = unit - b * H;
+  const int d = H * HD;
+  const int ctx = ctx_len[b];
+  const bf16* row = qkv + static_cast<size_t>(b) * 3 * d;
+  const int* bt = block_table + static_cast<size_t>(b) * cache.max_pages_per_row;
+  const uint32_t ks_u32 = ptx::smem_u32(Ks), vs_u32 = ptx::smem_u32(Vs);
+
+  auto issue_tile = [&](int t0) {   // all K and V chunks of tokens [t0, min(ctx, t0 + tile))
+    int n = ctx - t0;
+    if (n > tile) n = tile;
+    for (int i = tid; i < n * CH; i += kWideThreads) {
+      const int j = i / CH, c = i - j * CH, t = t0 + j;
+      const int page = bt[t / cache.page_tokens], tin = t % cache.page_tokens;
+      const bf16* kp = cache.base + kv_index(cache, layer, 0, page, h, tin) + c * 8;
+      const bf16* vp = cache.base + kv_index(cache, layer, 1, page, h, tin) + c * 8;
+      const uint32_t off = static_cast<uint32_t>(j) * (HD * 2) + c * 16;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ks_u32 + off), "l"(kp) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(vs_u32 + off), "l"(vp) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  issue_tile(0);
+
+  // ---- q / k_new / v_new: thread owns dims (2 tid, 2 tid + 1); rotary on q and k_new; append to the cache
+  float vnx = 0.f, vny = 0.f, s_part = 0.f;
+  if (2 * tid < HD) {
+    const int dim = 2 * tid;
+    float2 qf = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(row + h * HD + dim));
+    float2 kf = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(row + d + h * HD + dim));
+    const uint32_t vw = *reinterpret_cast<const uint32_t*>(row + 2 * d + h * HD + dim);
+    if (rotary_dim > 0 && dim < rotary_dim) {
+      rotary_pair(qf.x, qf.y, dim / 2, ctx, rotary_dim);
+      rotary_pair(kf.x, kf.y, dim / 2, ctx, rotary_dim);
+      kf = unpack_bf16x2(pack_bf16x2(kf.x, kf.y));  // exactly what later steps read back from the cache
+    }
+    const int page = bt[ctx / cache.page_tokens], tin = ctx % cache.page_tokens;
+    *reinterpret_cast<uint32_t*>(cache.base + kv_index(cache, layer, 0, page, h, tin) + dim) = pack_bf16x2(kf.x, kf.y);
+    *reinterpret_cast<uint32_t*>(cache.base + kv_index(cache, layer, 1, page, h, tin) + dim) = vw;
+    const float2 vf = unpack_bf16x2(vw);
+    vnx = vf.x; vny = vf.y;
+    qs[dim] = qf.x * scale;
+    qs[dim + 1] = qf.y * scale;
+    s_part = (qf.x * scale) * kf.x + (qf.y * scale) * kf.y;
+  }
+  s_part = warp_sum(s_part);
+  if (lane == 0) red[warp] = s_part;
+  __syncthreads();
+  float s_new = 0.f;
+#pragma unroll
+  for (int w = 0; w < NW; ++w) s_new += red[w];
+  // this lane's 8 query values for the score loop
+  const int grp = lane / CH, ch = lane - grp * CH;
+  float q8[8];
+  {
+    const float4 a0 = *reinterpret_cast<const float4*>(qs + ch * 8), a1 = *reinterpret_cast<const float4*>(qs + ch * 8 + 4);
+    q8[0] = a0.x; q8[1] = a0.y; q8[2] = a0.z; q8[3] = a0.w; q8[4] = a1.x; q8[5] = a1.y; q8[6] = a1.z; q8[7] = a1.w;
+  }
+
+  float m_run = s_new, l_run = 0.f, accx = 0.f, accy = 0.f;
+#pragma unroll 1
+  for (int t0 = 0; t0 < ctx; t0 += tile) {
+    int n = ctx - t0;
+    if (n > tile) n = tile;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();   // the tile has landed; (second tile on) the previous tile's red[] / sc[] reads are complete
+    // ---- scores of the tile
+    float mx = -INFINITY;
+    for (int j0 = warp * TPW; j0 < n; j0 += NW * TPW) {
+      const int j = j0 + grp;
+      float sdot = 0.f;
+      if (j < n) {
+        const uint4 kk = *reinterpret_cast<const uint4*>(Ks + static_cast<size_t>(j) * (HD * 2) + ch * 16);
+        const float2 k0 = unpack_bf16x2(kk.x), k1 = unpack_bf16x2(kk.y), k2 = unpack_bf16x2(kk.z), k3 = unpack_bf16x2(kk.w);
+        sdot = q8[0] * k0.x;
+        sdot = fmaf(q8[1], k0.y, sdot); sdot = fmaf(q8[2], k1.x, sdot); sdot = fmaf(q8[3], k1.y, sdot);
+        sdot = fmaf(q8[4], k2.x, sdot); sdot = fmaf(q8[5], k2.y, sdot); sdot = fmaf(q8[6], k3.x, sdot); sdot = fmaf(q8[7], k3.y, sdot);
+      }
+#pragma unroll
+      for (int o = CH / 2; o > 0; o >>= 1) sdot += __shfl_xor_sync(0xffffffffu, sdot, o);
+      if (j < n) {
+        if (ch == 0) sc[j] = sdot;
+        mx = fmaxf(mx, sdot);
+      }
+    }
+    mx = warp_max(mx);
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    float m_new = m_run;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) m_new = fmaxf(m_new, red[w]);
+    // ---- probabilities (each thread its own slots), their sum
+    float ls = 0.f;
+    for (int j = tid; j < n; j += kWideThreads) {
+      const float pr = expf(sc[j] - m_new);
+      sc[j] = pr;
+      ls += pr;
+    }
+    ls = warp_sum(ls);
+    if (lane == 0) red[NW + warp] = ls;
+    __syncthreads();
+    const float resc = expf(m_run - m_new);
+    float lt = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) lt += red[NW + w];
+    l_run = l_run * resc + lt;
+    m_run = m_new;
+    // ---- output dims of this thread over the tile
+    if (2 * tid < HD) {
+      float ax = 0.f, ay = 0.f;
+      const uint8_t* vcol = Vs + tid * 4;
+#pragma unroll 4
+      for (int j = 0; j < n; ++j) {
+        const float2 vf = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(vcol + static_cast<size_t>(j) * (HD * 2)));
+        const float pr = sc[j];
+        ax = fmaf(pr, vf.x, ax);
+        ay = fmaf(pr, vf.y, ay);
+      }
+      accx = accx * resc + ax;
+      accy = accy * resc + ay;
+    }
+    if (t0 + tile < ctx) {
+      __syncthreads();   // every thread is done with Ks / Vs / sc before the next tile overwrites them
+      issue_tile(t0 + tile);
+    }
+  }
+  // ---- the new token (m_run >= s_new by construction)
+  const float p_new = expf(s_new - m_run);
+  l_run += p_new;
+  if (2 * tid < HD) {
+    const float inv = 1.f / l_run;
+    const float o0 = (accx + p_new * vnx) * inv, o1 = (accy + p_new * vny) * inv;
+    *reinterpret_cast<uint32_t*>(out + static_cast<size_t>(b) * d + h * HD + 2 * tid) = pack_bf16x2(o0, o1);
+  }
+}
+
 }  // namespace
 
 int attention_prefill(const bf16* qkv, bf16* out, int B, int S, int H, int hd, float scale, int causal,
@@ -528,6 +691,47 @@ int attention_decode(const bf16* qkv, bf16* out, int B, int H, int hd, float sca
                      const int* block_table, const int* ctx_len, int rotary_dim, cudaStream_t s) {
   if (B <= 0) return 0;
   if (!cache) return (int)cudaErrorInvalidValue;
+  // One CTA per (row, head) for head_dim 256 (GPT-J); CCB_ATTN_WIDE=1 / 0 forces it on / off for every head_dim.
+  static const int wide_mode = [] {
+    const char* e = getenv("CCB_ATTN_WIDE");
+    return e ? (e[0] == '0' ? 0 : 1) : -1;
+  }();
+  if (wide_mode == 1 || (wide_mode == -1 && hd == 256)) {
+    // tile = tokens staged at once: the whole context when it fits (max_pages_per_row >= max_ctx), 96 KB of K + V at most
+    int tile = (cache->max_pages_per_row * cache->page_tokens + 15) & ~15;
+    const int cap = (96 * 1024) / (hd * 4);
+    if (tile > cap) tile = cap;
+    static const int forced_tile = [] {   // testing: a small tile exercises the online-softmax fold across tiles
+      const char* e = getenv("CCB_ATTN_WIDE_TILE");
+      return e ? atoi(e) : 0;
+    }();
+    if (forced_tile > 0 && forced_tile < tile) tile = forced_tile;
+    const size_t wsmem = static_cast<size_t>(tile) * hd * 4 + (hd + tile + 2 * (kWideThreads / 32)) * sizeof(float);
+#define CCB_LAUNCH_WIDE(HDV)                                                                                              \
+  do {                                                                                                                    \
+    static size_t configured = 0;                                                                                         \
+    if (wsmem > 48 * 1024 && wsmem > configured) {                                                                        \
+      cudaError_t e = cudaFuncSetAttribute(attention_decode_wide_kernel<HDV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                           112 * 1024);                                                                   \
+      if (e != cudaSuccess) return (int)e;                                                                                \
+      configured = 112 * 1024;                                                                                            \
+    }                                                                                                                     \
+    cudaError_t le = launch_kernel(attention_decode_wide_kernel<HDV>, dim3(B * H), dim3(kWideThreads), wsmem, s, true, qkv, \
+                                   out, B, H, scale, *cache, layer, block_table, ctx_len, rotary_dim, tile);              \
+    if (le != cudaSuccess) return (int)le;                                                                                \
+  } while (0)
+    if (hd == 64)
+      CCB_LAUNCH_WIDE(64);
+    else if (hd == 128)
+      CCB_LAUNCH_WIDE(128);
+    else if (hd == 256)
+      CCB_LAUNCH_WIDE(256);
+    else
+      return (int)cudaErrorInvalidValue;
+#undef CCB_LAUNCH_WIDE
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : (int)e;
+  }
   // per-warp shared memory: hd floats of q + one score per cached token
   const int sc_cap = (cache->max_pages_per_row + 3) & ~3;  // max_pages_per_row == max_ctx >= any context length
   const size_t smem = static_cast<size_t>(kDecodeWarps) * (hd + sc_cap) * sizeof(float);

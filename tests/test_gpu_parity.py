@@ -417,3 +417,15 @@ def test_batched_generate_loop_matches_reference(tiny_engine):
             if torch.is_tensor(w[3]):
                 assert torch.allclose(g[3].cpu(), w[3])
             assert torch.allclose(g[4].cpu(), w[4], atol=1e-4, rtol=1e-4)
+
+
+@pytest.mark.parametrize("tile", ["0", "5"])
+def test_cta_per_unit_decode_attention_on_the_fixtures(tile):
+    """attention_decode_wide_kernel (one CTA per (row, head), the GPT-J head_dim-256 path) forced on for every head_dim in a
+    child process: the GPT-J fixture's logits, greedy / beam / sampled captions must still equal the reference's; tile = 5
+    makes every context span several tiles (online-softmax fold)."""
+    import subprocess
+    env = dict(os.environ, CCB_ATTN_WIDE="1", CCB_ATTN_WIDE_TILE=tile, CCB_MEGA="0")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-k", "not cta_per_unit",
+                        "-p", "no:cacheprovider"], env=env, cwd=ROOT, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]

@@ -72,6 +72,28 @@ __global__ void __launch_bounds__(256, 1) bar_kernel(unsigned* ctr, unsigned* fl
         } while (!done);
       }
       __syncthreads();
+    } else if (V == 10) {  // V2 without the consumer-side fence: the data is read with ld.global.cg (L2) after the poll's branch
+      __syncthreads();
+      if (t == 0) { fence_acq_rel(); red_relaxed(ctr, 1); while (ld_relaxed(ctr) < (unsigned)it * n) {} }
+      __syncthreads();
+    } else if (V == 11) {  // V10 + every thread fences its own stores before the CTA barrier (t0's fence then finds nothing outstanding)
+      fence_acq_rel();
+      __syncthreads();
+      if (t == 0) { fence_acq_rel(); red_relaxed(ctr, 1); while (ld_relaxed(ctr) < (unsigned)it * n) {} }
+      __syncthreads();
+    } else if (V == 12) {  // V10 with the fence timed (clock64 around it, accumulated in flags[cta * 32 + 1])
+      __syncthreads();
+      if (t == 0) {
+        const long long c0 = clock64();
+        fence_acq_rel();
+        const long long c1 = clock64();
+        red_relaxed(ctr, 1);
+        while (ld_relaxed(ctr) < (unsigned)it * n) {}
+        const long long c2 = clock64();
+        flags[cta * 32 + 1] += (unsigned)(c1 - c0);
+        flags[cta * 32 + 2] += (unsigned)(c2 - c1);
+      }
+      __syncthreads();
     }
     // check: read what CTA (cta+1)%n wrote this iteration (through L2)
     float v;
@@ -107,7 +129,7 @@ int main() {
   cudaMemset(err, 0, 4);
   const int iters = 2000;
   // baseline: the fixed second barrier (variant 0 style) costs the same in every variant; report total per iteration
-  float t[10];
+  float t[13];
   run<0>(ctr, flags, data, err, 100);
   t[0] = run<0>(ctr, flags, data, err, iters);
   t[1] = run<1>(ctr, flags, data, err, iters);
@@ -119,12 +141,24 @@ int main() {
   t[7] = run<7>(ctr, flags, data, err, iters);
   t[8] = run<8>(ctr, flags, data, err, iters);
   t[9] = run<9>(ctr, flags, data, err, iters);
+  t[10] = run<10>(ctr, flags, data, err, iters);
+  t[11] = run<11>(ctr, flags, data, err, iters);
+  t[12] = run<12>(ctr, flags, data, err, iters);
+  {
+    unsigned hf[148 * 32];
+    cudaMemcpy(hf, flags, sizeof(hf), cudaMemcpyDeviceToHost);
+    double f = 0, w = 0;
+    for (int c = 0; c < 148; ++c) { f += hf[c * 32 + 1]; w += hf[c * 32 + 2]; }
+    printf("variant 12: fence.acq_rel.gpu after the data store %.0f cycles, red + poll until complete %.0f cycles (mean over CTAs and iterations)\n",
+           f / 148 / iters, w / 148 / iters);
+  }
   unsigned herr; cudaMemcpy(&herr, err, 4, cudaMemcpyDeviceToHost);
-  const char* names[10] = {"t0 red.release + ld.acquire poll", "relaxed poll + fence", "fence + red.relaxed, relaxed poll + fence",
-                          "8 pollers (lane 0 per warp)", "per-CTA flags, one warp reads all", "threadfence + atomicAdd + volatile poll", "8 counters, per-warp", "16 sharded counters, one warp polls", "8 sharded counters", "32 sharded counters"};
+  const char* names[13] = {"t0 red.release + ld.acquire poll", "relaxed poll + fence", "fence + red.relaxed, relaxed poll + fence",
+                          "8 pollers (lane 0 per warp)", "per-CTA flags, one warp reads all", "threadfence + atomicAdd + volatile poll", "8 counters, per-warp", "16 sharded counters, one warp polls", "8 sharded counters", "32 sharded counters",
+                          "fence + red.relaxed, relaxed poll, NO consumer fence", "per-thread fences before the CTA barrier + V10", "V10 with the fence timed"};
   // every iteration = variant barrier + one V0-style barrier: V0 total / 2 = cost of one V0 barrier
   const float v0 = t[0] / iters / 2 * 1000;
-  for (int i = 0; i < 10; ++i) printf("variant %d (%s): %.3f us per barrier\n", i, names[i], t[i] / iters * 1000 - v0);
+  for (int i = 0; i < 13; ++i) printf("variant %d (%s): %.3f us per barrier\n", i, names[i], t[i] / iters * 1000 - v0);
   printf("ordering errors: %u (%s)\n", herr, cudaGetErrorString(cudaGetLastError()));
   return 0;
 }

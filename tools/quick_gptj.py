@@ -18,7 +18,11 @@ torch.cuda.empty_cache()
 print("engine ready in %.1fs, device bytes %.2f GB" % (time.time() - t0, eng.device_bytes / 1e9))
 images = synthetic.synthetic_images(B, cfg, device="cuda")
 p = eng.gen_params("sample", T, stop_token=-1, max_stops=0, top_p=0.9, seed=1)
+profile_last = os.environ.get("CCB_PROFILE_LAST") == "1"
 for it in range(3):
+    if profile_last and it == 2:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -29,4 +33,6 @@ for it in range(3):
     ms = e0.elapsed_time(e1)
     print("iter %d: total %.2f ms (%.0f captions/s) prefill+first %.2f ms decode %.2f ms (%d steps, %.3f ms/step)" % (
         it, ms, B / ms * 1e3, pre, dec, steps, dec / max(steps, 1)))
+if profile_last:
+    torch.cuda.profiler.stop()
 print(tokens[0].tolist()[:16])
