@@ -38,6 +38,15 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
   }
   return ctr;
 }
+// the four Exp(1) values of elements 4 g .. 4 g + 3 (one Philox call; identical to philox_exp1 of each element)
+__device__ __forceinline__ float4 philox_exp1_x4(unsigned long long seed, unsigned long long row, uint32_t step, uint32_t g) {
+  const uint4 c = make_uint4(g, step, static_cast<uint32_t>(row), static_cast<uint32_t>(row >> 32));
+  const uint2 k = make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+  const uint4 r = philox4x32_10(c, k);
+  const float sc = 1.0f / 16777216.0f;
+  return make_float4(-logf((static_cast<float>(r.x >> 8) + 0.5f) * sc), -logf((static_cast<float>(r.y >> 8) + 0.5f) * sc),
+                     -logf((static_cast<float>(r.z >> 8) + 0.5f) * sc), -logf((static_cast<float>(r.w >> 8) + 0.5f) * sc));
+}
 __device__ __forceinline__ float philox_exp1(unsigned long long seed, unsigned long long row, uint32_t step,
                                              uint32_t v) {
   const uint4 c = make_uint4(v >> 2, step, static_cast<uint32_t>(row), static_cast<uint32_t>(row >> 32));
@@ -269,14 +278,34 @@ __device__ SelectResult radix_select(const float* vals, int V, int mode, int kth
         }
       }
     }
+    // the 16 (count, mass) pairs of all threads -> block totals with ONE pair of CTA barriers: shuffle tree inside a
+    // warp, then thread b adds the warps' totals of bin b in warp order (a fixed order: deterministic masses)
+    {
+      __shared__ int warp_cnt[32][16];
+      __shared__ double warp_mass[32][16];
+      const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
 #pragma unroll
-    for (int b = 0; b < 16; ++b) {
-      const int cb = block_sum_i(c[b], iscratch);
-      double mb = 0.0;
-      if (mode != 0) mb = block_sum_d(m[b], dscratch);
-      if (threadIdx.x == 0) {
-        bin_cnt[b] = cb;
-        bin_mass[b] = mb;
+      for (int b = 0; b < 16; ++b) {
+        int cb = c[b];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cb += __shfl_xor_sync(0xffffffffu, cb, o);
+        double mb = 0.0;
+        if (mode != 0) mb = warp_sum_d(m[b]);
+        if (lane == 0) {
+          warp_cnt[w][b] = cb;
+          warp_mass[w][b] = mb;
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x < 16) {
+        int cb = 0;
+        double mb = 0.0;
+        for (int ww = 0; ww < nw; ++ww) {
+          cb += warp_cnt[ww][threadIdx.x];
+          mb += warp_mass[ww][threadIdx.x];
+        }
+        bin_cnt[threadIdx.x] = cb;
+        bin_mass[threadIdx.x] = mb;
       }
     }
     __syncthreads();
@@ -484,15 +513,38 @@ __global__ void __launch_bounds__(kSampThreads) top_p_kernel(const TopPArgs a) {
   ArgMax best;
   best.v = -INFINITY;
   best.i = 0x7fffffff;
-  for (int v = threadIdx.x; v < V; v += blockDim.x) {
-    const float x = vals[v];
-    if (x == -INFINITY) continue;
-    const float p = expf(x - mx) / ksum;
-    const float q = qrow ? qrow[v] : philox_exp1(a.seed, rid, step, v);
-    ArgMax c;
-    c.v = p / q;
-    c.i = v;
-    best = argmax_better(best, c);
+  if (qrow != nullptr) {
+    for (int v = threadIdx.x; v < V; v += blockDim.x) {
+      const float x = vals[v];
+      if (x == -INFINITY) continue;
+      const float p = expf(x - mx) / ksum;
+      ArgMax c;
+      c.v = p / qrow[v];
+      c.i = v;
+      best = argmax_better(best, c);
+    }
+  } else {
+    // a thread takes the four elements that share one Philox block (the noise of element v is word v & 3 of block v >> 2)
+    for (int g = threadIdx.x; 4 * g < V; g += blockDim.x) {
+      float x[4];
+      bool any = false;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        x[k] = (4 * g + k < V) ? vals[4 * g + k] : -INFINITY;
+        any |= x[k] != -INFINITY;
+      }
+      if (!any) continue;
+      const float4 q4 = philox_exp1_x4(a.seed, rid, step, static_cast<uint32_t>(g));
+      const float q[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (x[k] == -INFINITY) continue;
+        ArgMax c;
+        c.v = (expf(x[k] - mx) / ksum) / q[k];
+        c.i = 4 * g + k;
+        best = argmax_better(best, c);
+      }
+    }
   }
   const ArgMax win = block_argmax(best, ascratch);
   if (threadIdx.x == 0) a.next[b] = win.i;
