@@ -28,6 +28,8 @@ import time
 
 import torch
 
+_OUT = sys.stdout   # main() points it at the original stdout and redirects fd 1 to stderr
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -176,7 +178,7 @@ def run_reference(args):
         "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "device": "host CPU"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0}))
+        "gpu_launches": 0}), file=_OUT, flush=True)
 
 
 def cpu_baseline_leg():
@@ -205,6 +207,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    # stdout carries the JSON line and nothing else: whatever libraries print meanwhile (the "NCCL version ..." banner
+    # of a box with NCCL_DEBUG set, ...) is sent to stderr
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
         return
@@ -312,7 +320,7 @@ def main():
                          "bytes_per_launch": step_bytes, "ms_per_launch": step_ms, "peak_source": peak_src},
             "cpu_baseline": cpu,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), file=_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
