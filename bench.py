@@ -280,7 +280,12 @@ def main():
     if rank == 0:
         sampler.start()
     l0 = eng.launch_count
+    profiled = os.environ.get("CCB_BENCH_PROFILE") == "1"   # `ncu --profile-from-start off`: the launch list of the timed region
+    if profiled:
+        torch.cuda.profiler.start()
     ms_total, (tokens, lengths) = timed(step_resident, args.steps)
+    if profiled:
+        torch.cuda.profiler.stop()
     launches = eng.launch_count - l0
     n_sum = min(args.steps, 64)
     prefill_ms, decode_ms, decode_steps = eng.timing_sum(n_sum)
