@@ -159,7 +159,7 @@ template <int NT, int KS>   // NT: key tiles of 8 (even, >= 2 * warps); KS: head
 __global__ void __launch_bounds__(256) attention_prefill_mma_kernel(
     const bf16* __restrict__ qkv, bf16* __restrict__ out, int S, int H, int hd, float scale, int causal,
     KvCache cache, int layer, const int* __restrict__ block_table, int pos0, int write_cache,
-    const uint8_t* __restrict__ key_mask) {
+    const uint8_t* __restrict__ key_mask, int rotary_dim) {
   extern __shared__ uint4 smem_u4[];
   const int h = blockIdx.x, b = blockIdx.y;
   const int d = H * hd;
@@ -183,6 +183,17 @@ __global__ void __launch_bounds__(256) attention_prefill_mma_kernel(
       const bf16* rowp = base + static_cast<size_t>(j) * 3 * d + h * hd + c * 8;
       kk = *reinterpret_cast<const uint4*>(rowp + d);
       vv = *reinterpret_cast<const uint4*>(rowp + 2 * d);
+      if (c * 8 < rotary_dim) {   // GPT-J rotary on the first rotary_dim dims of K (pairs 2i, 2i+1), rounded to bf16 as cached
+        uint32_t* kw = reinterpret_cast<uint32_t*>(&kk);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (c * 8 + 2 * e < rotary_dim) {
+            float2 kf = unpack_bf16x2(kw[e]);
+            rotary_pair(kf.x, kf.y, c * 4 + e, pos0 + j, rotary_dim);
+            kw[e] = pack_bf16x2(kf.x, kf.y);
+          }
+        }
+      }
       if (write_cache) {
         const int pos = pos0 + j;
         const int page = block_table[static_cast<size_t>(b) * cache.max_pages_per_row + pos / cache.page_tokens];
@@ -214,6 +225,18 @@ __global__ void __launch_bounds__(256) attention_prefill_mma_kernel(
       qf[ks][1] = (row_b < S && k0 < hd) ? *reinterpret_cast<const uint32_t*>(qb + k0) : 0u;
       qf[ks][2] = (row_a < S && k1 < hd) ? *reinterpret_cast<const uint32_t*>(qa + k1) : 0u;
       qf[ks][3] = (row_b < S && k1 < hd) ? *reinterpret_cast<const uint32_t*>(qb + k1) : 0u;
+      if (ks * 16 < rotary_dim) {   // rotary on q (the MMA operand is bf16: the rotated pair is rounded once more)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int k = (e < 2) ? k0 : k1;
+          const int row = (e & 1) ? row_b : row_a;
+          if (k < rotary_dim && row < S) {
+            float2 f = unpack_bf16x2(qf[ks][e]);
+            rotary_pair(f.x, f.y, k >> 1, pos0 + row, rotary_dim);
+            qf[ks][e] = pack_bf16x2(f.x, f.y);
+          }
+        }
+      }
     }
   }
   // ---- scores = Q K^T
@@ -321,7 +344,8 @@ __global__ void __launch_bounds__(256) attention_prefill_mma_kernel(
 
 template <int NT, int KS>
 int launch_prefill_mma(const bf16* qkv, bf16* out, int B, int S, int H, int hd, float scale, int causal, const KvCache& c,
-                       int layer, const int* block_table, int pos0, int write_cache, const uint8_t* key_mask, cudaStream_t s) {
+                       int layer, const int* block_table, int pos0, int write_cache, const uint8_t* key_mask, int rotary_dim,
+                       cudaStream_t s) {
   const int HDP = KS * 16 + 8, S16 = NT * 8;
   const size_t smem = static_cast<size_t>(2) * S16 * HDP * sizeof(bf16) + S16 * sizeof(float);
   static size_t configured = 0;
@@ -332,17 +356,17 @@ int launch_prefill_mma(const bf16* qkv, bf16* out, int B, int S, int H, int hd, 
   }
   const int warps = (S + 15) / 16;
   cudaError_t e = launch_kernel(attention_prefill_mma_kernel<NT, KS>, dim3(H, B), dim3(warps * 32), smem, s, true, qkv, out, S, H, hd,
-                                scale, causal, c, layer, block_table, pos0, write_cache, key_mask);
+                                scale, causal, c, layer, block_table, pos0, write_cache, key_mask, rotary_dim);
   return e == cudaSuccess ? 0 : (int)e;
 }
 
 template <int NT>
 int dispatch_prefill_mma_ks(int ks, const bf16* qkv, bf16* out, int B, int S, int H, int hd, float scale, int causal,
-                            const KvCache& c, int layer, const int* bt, int pos0, int wc, const uint8_t* km, cudaStream_t s) {
-  if (ks <= 4) return launch_prefill_mma<NT, 4>(qkv, out, B, S, H, hd, scale, causal, c, layer, bt, pos0, wc, km, s);
-  if (ks <= 8) return launch_prefill_mma<NT, 8>(qkv, out, B, S, H, hd, scale, causal, c, layer, bt, pos0, wc, km, s);
-  if (ks <= 13) return launch_prefill_mma<NT, 13>(qkv, out, B, S, H, hd, scale, causal, c, layer, bt, pos0, wc, km, s);
-  return launch_prefill_mma<NT, 16>(qkv, out, B, S, H, hd, scale, causal, c, layer, bt, pos0, wc, km, s);
+                            const KvCache& c, int layer, const int* bt, int pos0, int wc, const uint8_t* km, int rd, cudaStream_t s) {
+  if (ks <= 4) return launch_prefill_mma<NT, 4>(qkv, out, B, S, H, hd, scale, causal, c, layer, bt, pos0, wc, km, rd, s);
+  if (ks <= 8) return launch_prefill_mma<NT, 8>(qkv, out, B, S, H, hd, scale, causal, c, layer, bt, pos0, wc, km, rd, s);
+  if (ks <= 13) return launch_prefill_mma<NT, 13>(qkv, out, B, S, H, hd, scale, causal, c, layer, bt, pos0, wc, km, rd, s);
+  return launch_prefill_mma<NT, 16>(qkv, out, B, S, H, hd, scale, causal, c, layer, bt, pos0, wc, km, rd, s);
 }
 
 // ------------------------------------------------------------------------------------------------ decode
@@ -657,16 +681,16 @@ int attention_prefill(const bf16* qkv, bf16* out, int B, int S, int H, int hd, f
     const char* e = getenv("CCB_ATTN_MMA");
     return !(e && e[0] == '0');
   }();
-  if (use_mma && S <= 128 && hd % 8 == 0 && hd <= 256 && rotary_dim == 0) {
+  if (use_mma && S <= 128 && hd % 8 == 0 && hd <= 256 && rotary_dim % 2 == 0) {
     KvCache c;
     if (cache) c = *cache;
     const int wc = cache != nullptr ? 1 : 0;
     const int ks = (hd + 15) / 16, nt = 2 * ((S + 15) / 16);
-    if (nt <= 4) return dispatch_prefill_mma_ks<4>(ks, qkv, out, B, S, H, hd, scale, causal, c, layer, block_table, pos0, wc, key_mask, s);
-    if (nt <= 6) return dispatch_prefill_mma_ks<6>(ks, qkv, out, B, S, H, hd, scale, causal, c, layer, block_table, pos0, wc, key_mask, s);
-    if (nt <= 8) return dispatch_prefill_mma_ks<8>(ks, qkv, out, B, S, H, hd, scale, causal, c, layer, block_table, pos0, wc, key_mask, s);
-    if (nt <= 10) return dispatch_prefill_mma_ks<10>(ks, qkv, out, B, S, H, hd, scale, causal, c, layer, block_table, pos0, wc, key_mask, s);
-    return dispatch_prefill_mma_ks<16>(ks, qkv, out, B, S, H, hd, scale, causal, c, layer, block_table, pos0, wc, key_mask, s);
+    if (nt <= 4) return dispatch_prefill_mma_ks<4>(ks, qkv, out, B, S, H, hd, scale, causal, c, layer, block_table, pos0, wc, key_mask, rotary_dim, s);
+    if (nt <= 6) return dispatch_prefill_mma_ks<6>(ks, qkv, out, B, S, H, hd, scale, causal, c, layer, block_table, pos0, wc, key_mask, rotary_dim, s);
+    if (nt <= 8) return dispatch_prefill_mma_ks<8>(ks, qkv, out, B, S, H, hd, scale, causal, c, layer, block_table, pos0, wc, key_mask, rotary_dim, s);
+    if (nt <= 10) return dispatch_prefill_mma_ks<10>(ks, qkv, out, B, S, H, hd, scale, causal, c, layer, block_table, pos0, wc, key_mask, rotary_dim, s);
+    return dispatch_prefill_mma_ks<16>(ks, qkv, out, B, S, H, hd, scale, causal, c, layer, block_table, pos0, wc, key_mask, rotary_dim, s);
   }
   const size_t smem = (static_cast<size_t>(S) * (hd / 2 + 1) + static_cast<size_t>(S) * (hd / 2) + 1) * 4 +
                       static_cast<size_t>(kPrefillWarps) * (hd + S) * 4;
