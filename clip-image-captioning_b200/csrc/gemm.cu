@@ -296,6 +296,15 @@ int gemm_launch(const GemmArgs& a, const GemmWorkspace& w, cudaStream_t stream) 
       split = slots / tiles;
       const int max_by_k = p.k_blocks / 4 > 0 ? p.k_blocks / 4 : 1;
       if (split > max_by_k) split = max_by_k;
+      // with two CTAs per SM, clusters of 3, 5, 6 or 7 CTAs place badly on the GPCs (the 96-tile x 3 q/k/v GEMM of a 16-row
+      // GPT-J step: 32 us against 26 us with pairs; GPT-J step 3.02 -> 2.91 ms): round the split down to a power of two.
+      // One CTA per SM (64-token tiles: the GPT2-XL operator chain) is 2 % faster with the odd splits, so it keeps them.
+      static const bool pow2 = [] {
+        const char* e = getenv("CCB_GEMM_SPLIT_ANY");
+        return !(e && e[0] == '1');
+      }();
+      if (pow2 && bn == 32)
+        while (split & (split - 1)) --split;
     }
   }
   if (split > p.k_blocks) split = p.k_blocks;
