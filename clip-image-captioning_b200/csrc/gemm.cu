@@ -294,7 +294,11 @@ int gemm_launch(const GemmArgs& a, const GemmWorkspace& w, cudaStream_t stream) 
     const int slots = w.num_sms * (bn == 32 ? 2 : 1);
     if (tiles < slots) {
       split = slots / tiles;
-      const int max_by_k = p.k_blocks / 4 > 0 ? p.k_blocks / 4 : 1;
+      static const int min_kb = [] {   // k-blocks a split must own at least (tuning: CCB_GEMM_MINKB)
+        const char* e = getenv("CCB_GEMM_MINKB");
+        return e && atoi(e) > 0 ? atoi(e) : 4;
+      }();
+      const int max_by_k = p.k_blocks / min_kb > 0 ? p.k_blocks / min_kb : 1;
       if (split > max_by_k) split = max_by_k;
       // with two CTAs per SM, clusters of 3, 5, 6 or 7 CTAs place badly on the GPCs (the 96-tile x 3 q/k/v GEMM of a 16-row
       // GPT-J step: 32 us against 26 us with pairs; GPT-J step 3.02 -> 2.91 ms): round the split down to a power of two.
