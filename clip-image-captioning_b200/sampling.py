@@ -209,3 +209,23 @@ def generate(model, inputs: Optional[torch.Tensor], encoder_hidden_states, encod
     if inputs.size(0) > 0:
         results.append([inputs, min_length, max_length, top_p, eos_probs])
     return results
+
+
+def unique_captions(outputs, num_prompt_tokens: int = 0, special_ids=(), unique: bool = True):
+    """The collection step of `sample` (sampling.py:311-323) on token ids: walks the result groups of `generate` in order,
+    strips the prompt and the special ids (what `tokenizer.decode(o, skip_special_tokens=True)[len(prompt):]` removes before
+    the comparison) and keeps the first occurrence of every caption with its [min_length, max_length, top_p] and EOS
+    log-probabilities.  As in the reference, nothing is collected when `unique` is false (`if unique and ... not in
+    captions`).  Returns (captions as id tuples, parameters, stats)."""
+    special = set(int(t) for t in special_ids)
+    captions, parameters, stats = [], [], []
+    for group in outputs:
+        tokens, min_len, max_len, top_p, eos_probs = group[0], group[1], group[2], group[3], group[4]
+        for i, row in enumerate(tokens.tolist()):
+            cap = tuple(t for t in row[num_prompt_tokens:] if t not in special)
+            if unique and cap not in captions:
+                captions.append(cap)
+                tp = top_p[i].item() if torch.is_tensor(top_p) else top_p
+                parameters.append([int(min_len[i]), int(max_len[i]), tp])
+                stats.append({"eos_prob": eos_probs[i], "tokens": row[num_prompt_tokens:]})
+    return captions, parameters, stats

@@ -213,3 +213,16 @@ def test_clip_text_tower_and_cos_sim_match_reference():
     assert (feats - fx["text_features"]).abs().max().item() <= 1e-4 * fx["text_features"].abs().max().item()
     sims = orc.cos_sim(feats, fx["image_features"])
     assert (sims - fx["sims"]).abs().max().item() <= 1e-5
+
+
+def test_unique_captions_collects_first_occurrences():
+    """The id-level restatement of sampling.py:311-323 (`sample`'s dedupe of the generate groups)."""
+    import clipcap_b200.sampling as S
+    g1 = [torch.tensor([[7, 8, 1, 2, 99], [7, 8, 3, 4, 99]]), torch.tensor([2, 3]), torch.tensor([9, 9]), torch.tensor([0.5, 0.7]),
+          torch.zeros(2, 3)]
+    g2 = [torch.tensor([[7, 8, 1, 2, 99, 99], [7, 8, 5, 99, 99, 99]]), torch.tensor([2, 2]), torch.tensor([8, 8]), 0.9, torch.ones(2, 4)]
+    caps, params, stats = S.unique_captions([g1, g2], num_prompt_tokens=2, special_ids=[99])
+    assert caps == [(1, 2), (3, 4), (5,)]
+    assert params == [[2, 9, 0.5], [3, 9, pytest.approx(0.7)], [2, 8, 0.9]]
+    assert [s["tokens"] for s in stats] == [[1, 2, 99], [3, 4, 99], [5, 99, 99, 99]]
+    assert S.unique_captions([g1, g2], 2, [99], unique=False) == ([], [], [])
