@@ -44,18 +44,21 @@ class CaptionSamplerBase:  # evaluate_model.py:355-367
 
 
 class NoBeamCaptionSampler(CaptionSamplerBase):  # evaluate_model.py:370-385
-    def __init__(self, top_p_values=(0.1,), temperature: float = 1.0, repetition_penalty: float = 1.2, seed: int = 0):
+    def __init__(self, top_p_values=(0.1,), temperature: float = 1.0, repetition_penalty: float = 1.2, seed: int = 0,
+                 max_decode_length: int = 75):
         self.top_p_values = list(top_p_values)
         self.temperature = temperature
         self.repetition_penalty = repetition_penalty
         self.seed = seed
+        self.max_decode_length = max_decode_length   # (the reference takes generate_no_beam's default, 75)
 
     def get_description(self):
         return f'NoBeam(rep_p={self.repetition_penalty}, temp={self.temperature}, top_p={self.top_p_values})'
 
     def generate_captions(self, model, prefix, image_embedding, image):
         return generate_no_beam(model, prefix, top_p_values=self.top_p_values, temperature=self.temperature,
-                                repetition_penalty=self.repetition_penalty, seed=self.seed)
+                                repetition_penalty=self.repetition_penalty, seed=self.seed,
+                                max_decode_length=self.max_decode_length)
 
 
 class BeamCaptionSampler(CaptionSamplerBase):
