@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libclipcap_b200.so")
 DTYPE_F32, DTYPE_F16, DTYPE_BF16 = 0, 1, 2
 LM_GPT2, LM_GPTJ = 0, 1
 MAP_NONE, MAP_TRANSFORMER, MAP_MLP, MAP_TRANSFORMER_ALL = 0, 1, 2, 3
-ACT = {"none": 0, "relu": 1, "quick_gelu": 2, "gelu_new": 3, "gelu": 4, "elu": 5, "selu": 6, "tanh": 7}
+ACT = {"none": 0, "relu": 1, "quick_gelu": 2, "gelu_new": 3, "gelu": 4, "elu": 5, "selu": 6, "tanh": 7, "geglu": 8}
 GEN_GREEDY, GEN_SAMPLE, GEN_BEAM = 0, 1, 2
 
 

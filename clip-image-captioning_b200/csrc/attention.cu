@@ -348,7 +348,8 @@ int launch_prefill_mma(const bf16* qkv, bf16* out, int B, int S, int H, int hd, 
                        cudaStream_t s) {
   const int HDP = KS * 16 + 8, S16 = NT * 8;
   const size_t smem = static_cast<size_t>(2) * S16 * HDP * sizeof(bf16) + S16 * sizeof(float);
-  static size_t configured = 0;
+  static size_t configured_dev[kMaxDevices] = {};
+  size_t& configured = configured_dev[current_device_slot()];
   if (smem > 48 * 1024 && smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(attention_prefill_mma_kernel<NT, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return (int)e;
@@ -695,7 +696,8 @@ int attention_prefill(const bf16* qkv, bf16* out, int B, int S, int H, int hd, f
   const size_t smem = (static_cast<size_t>(S) * (hd / 2 + 1) + static_cast<size_t>(S) * (hd / 2) + 1) * 4 +
                       static_cast<size_t>(kPrefillWarps) * (hd + S) * 4;
   if (smem > 200 * 1024) return (int)cudaErrorInvalidValue;
-  static size_t configured = 0;
+  static size_t configured_dev[kMaxDevices] = {};
+  size_t& configured = configured_dev[current_device_slot()];
   if (smem > 48 * 1024 && smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(attention_prefill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          200 * 1024);
@@ -733,7 +735,8 @@ int attention_decode(const bf16* qkv, bf16* out, int B, int H, int hd, float sca
     const size_t wsmem = static_cast<size_t>(tile) * hd * 4 + (hd + tile + 2 * (kWideThreads / 32)) * sizeof(float);
 #define CCB_LAUNCH_WIDE(HDV)                                                                                              \
   do {                                                                                                                    \
-    static size_t configured = 0;                                                                                         \
+    static size_t configured_dev[kMaxDevices] = {};                                                                       \
+    size_t& configured = configured_dev[current_device_slot()];                                                           \
     if (wsmem > 48 * 1024 && wsmem > configured) {                                                                        \
       cudaError_t e = cudaFuncSetAttribute(attention_decode_wide_kernel<HDV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                            112 * 1024);                                                                   \
@@ -763,7 +766,8 @@ int attention_decode(const bf16* qkv, bf16* out, int B, int H, int hd, float sca
   const int grid = (B * H + kDecodeWarps - 1) / kDecodeWarps;
 #define CCB_LAUNCH_DECODE(HDV)                                                                                      \
   do {                                                                                                              \
-    static size_t configured = 0;                                                                                   \
+    static size_t configured_dev[kMaxDevices] = {};                                                                 \
+    size_t& configured = configured_dev[current_device_slot()];                                                     \
     if (smem > 48 * 1024 && smem > configured) {                                                                    \
       cudaError_t e = cudaFuncSetAttribute(attention_decode_kernel<HDV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                            200 * 1024);                                                             \

@@ -239,6 +239,13 @@ int block_forward(ccb_ctx* c, const Block& b, int M, const BlockShape& sh, AttnF
   RUN(attn());
   RUN(linear(c, c->att, d, M, b.proj, CCB_ACT_NONE, c->h, d, c->h, d, 0, s));
   if (!sh.parallel) RUN(layernorm_f32_bf16(c->h, d, b.ln2.g, b.ln2.b, sh.eps, c->x, d, M, d, s));
+  if (sh.act == CCB_ACT_GEGLU) {
+    // fc1 is 2 x hidden wide (layers/Transformer.py:74); the gated product overwrites the first half of every row
+    RUN(linear(c, c->x, d, M, b.fc, CCB_ACT_NONE, nullptr, 0, c->mlp, 2 * sh.hidden, 1, s));
+    RUN(geglu_inplace(c->mlp, 2 * sh.hidden, M, sh.hidden, s));
+    RUN(linear(c, c->mlp, 2 * sh.hidden, M, b.fc2, CCB_ACT_NONE, c->h, d, c->h, d, 0, s));
+    return 0;
+  }
   RUN(linear(c, c->x, d, M, b.fc, sh.act, nullptr, 0, c->mlp, sh.hidden, 1, s));
   RUN(linear(c, c->mlp, sh.hidden, M, b.fc2, CCB_ACT_NONE, c->h, d, c->h, d, 0, s));
   return 0;
@@ -307,7 +314,7 @@ int text_forward(ccb_ctx* c, const int32_t* tokens, int B, float* feat_out, cuda
   const int w = D.text_width, S = D.text_ctx, M = B * S, H = D.text_heads, hd = w / H;
   text_positions_eot_kernel<<<B, 128, 0, s>>>(tokens, S, c->txt_positions, c->txt_eot);
   RUN(launch_check());
-  RUN(embed_tokens(c->txt_wte, c->txt_wpe, tokens, c->txt_positions, c->h, M, w, s));
+  RUN(embed_tokens(c->txt_wte, c->txt_wpe, tokens, c->txt_positions, c->h, M, w, D.text_vocab, D.text_ctx, s));
   BlockShape sh{w, 4 * w, CCB_ACT_QUICKGELU, 1e-5f, false};
   const float scale = 1.0f / sqrtf(static_cast<float>(hd));
   for (int l = 0; l < D.text_layers; ++l) {
@@ -532,7 +539,7 @@ int lm_decode_step(ccb_ctx* c, int rows, cudaStream_t s) {
     RUN(linear(c, c->x, d, rows, c->lm_head, CCB_ACT_NONE, nullptr, 0, c->logits, c->ldv, 0, s));
     return 0;
   }
-  RUN(embed_tokens(c->wte, D.lm_arch == CCB_LM_GPT2 ? c->wpe : nullptr, c->next_tokens, c->ctx_len, c->h, rows, d, s));
+  RUN(embed_tokens(c->wte, D.lm_arch == CCB_LM_GPT2 ? c->wpe : nullptr, c->next_tokens, c->ctx_len, c->h, rows, d, D.lm_vocab, D.lm_n_pos, s));
   const BlockShape sh = lm_shape(D);
   const float scale = 1.0f / sqrtf(static_cast<float>(hd));
   for (int l = 0; l < D.lm_layers; ++l) {
@@ -732,6 +739,19 @@ bool starts_with(const char* s, const char* prefix, const char** rest) {
 // ================================================================================================ C ABI
 extern "C" {
 
+// Every entry point runs with the context's device current (launches, function attributes and event calls are per device)
+// and restores the caller's device on the way out.
+struct DeviceGuard {
+  int prev = -1, dev;
+  explicit DeviceGuard(int d) : dev(d) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    if (prev >= 0 && prev != dev) cudaSetDevice(prev);
+  }
+};
+
 const char* ccb_last_error(const ccb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err; }
 
 int64_t ccb_device_bytes(const ccb_ctx* ctx) { return ctx ? ctx->device_bytes : 0; }
@@ -739,7 +759,7 @@ int64_t ccb_launch_count(const ccb_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 void ccb_destroy(ccb_ctx* c) {
   if (!c) return;
-  cudaSetDevice(c->device);
+  DeviceGuard dev_guard(c->device);
   cudaDeviceSynchronize();
   for (auto& kvp : c->graphs) cudaGraphExecDestroy(kvp.second.exec);
   for (void* p : c->allocs) cudaFree(p);
@@ -764,7 +784,11 @@ int ccb_create(ccb_ctx** out, const ccb_model_desc* desc, int device) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(nullptr, "ccb_create: cudaGetDeviceProperties failed");
   if (prop.major != 10) return fail(nullptr, "ccb_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
-  if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, "ccb_create: cudaSetDevice failed");
+  DeviceGuard dev_guard(device);   // (the caller's current device is restored on return)
+  {
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess || cur != device) return fail(nullptr, "ccb_create: cudaSetDevice failed");
+  }
 
   const ccb_model_desc& D = *desc;
   if (D.lm_d <= 0 || D.lm_layers <= 0 || D.lm_heads <= 0 || D.lm_vocab <= 0 || D.lm_d % D.lm_heads)
@@ -773,6 +797,8 @@ int ccb_create(ccb_ctx** out, const ccb_model_desc* desc, int device) {
   const int lm_hd = D.lm_d / D.lm_heads;
   if (lm_hd != 64 && lm_hd != 128 && lm_hd != 256) return fail(nullptr, "ccb_create: LM head_dim %d unsupported (64/128/256)", lm_hd);
   if (D.lm_arch != CCB_LM_GPT2 && D.lm_arch != CCB_LM_GPTJ) return fail(nullptr, "ccb_create: unknown lm_arch");
+  if (D.lm_arch == CCB_LM_GPT2 && D.max_ctx > D.lm_n_pos)
+    return fail(nullptr, "ccb_create: max_ctx=%d exceeds the model's %d learned positions (wpe)", D.max_ctx, D.lm_n_pos);
   if (D.max_images <= 0 || D.max_beam <= 0 || D.max_ctx <= 0 || D.max_lm_tokens <= 0 || D.page_tokens <= 0)
     return fail(nullptr, "ccb_create: capacities must be positive");
   if ((D.map_kind == CCB_MAP_TRANSFORMER || D.map_kind == CCB_MAP_TRANSFORMER_ALL) && (D.map_heads <= 0 || D.lm_d % D.map_heads || (D.lm_d / D.map_heads) % 2 ||
@@ -873,7 +899,7 @@ int ccb_create(ccb_ctx** out, const ccb_model_desc* desc, int device) {
       slot_ln(c, base + ".norm2", b.ln2, d);
       make_linear(c, a, b.qkv, 3 * d, d, false);
       make_linear(c, a, b.proj, d, d, true);
-      make_linear(c, a, b.fc, D.map_hidden, d, true);
+      make_linear(c, a, b.fc, (D.map_act == CCB_ACT_GEGLU ? 2 : 1) * D.map_hidden, d, true);
       make_linear(c, a, b.fc2, d, D.map_hidden, true);
       // to_queries [d, d] -> rows [0, d); to_keys_values [2d, d] -> rows [d, 3d): keys then values
       // (layers/MultiHeadAttention.py:24-30).  The projections are bias-free by default (Transformer.py:91,96).
@@ -971,7 +997,8 @@ int ccb_create(ccb_ctx** out, const ccb_model_desc* desc, int device) {
   if (D.text_present) M = std::max(M, D.max_texts * D.text_ctx);
   c->max_rows_tokens = M;
   c->dmax = std::max(d, std::max(D.vit_present ? D.vit_width : 0, D.text_present ? D.text_width : 0));
-  c->hidden_max = std::max(4 * d, std::max(D.map_kind != CCB_MAP_NONE ? D.map_hidden : 0, D.vit_present ? 4 * D.vit_width : 0));
+  c->hidden_max = std::max(4 * d, std::max(D.map_kind != CCB_MAP_NONE ? (D.map_act == CCB_ACT_GEGLU ? 2 : 1) * D.map_hidden : 0,
+                                           D.vit_present ? 4 * D.vit_width : 0));
   if (D.text_present) c->hidden_max = std::max(c->hidden_max, 4 * D.text_width);
   const size_t Mz = static_cast<size_t>(M);
   c->h = a.arr<float>(Mz * c->dmax);
@@ -1105,6 +1132,7 @@ int ccb_create(ccb_ctx** out, const ccb_model_desc* desc, int device) {
 int ccb_load_weight(ccb_ctx* c, const char* name, const void* dev_ptr, int dtype, const int64_t* shape, int ndim,
                     void* stream) {
   if (!c || !name || !dev_ptr || !shape) return fail(c, "ccb_load_weight: null argument");
+  DeviceGuard dev_guard(c->device);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   // normalise the reference's module prefixes
   std::string key;
@@ -1143,6 +1171,7 @@ int ccb_load_weight(ccb_ctx* c, const char* name, const void* dev_ptr, int dtype
 
 int ccb_weights_complete(ccb_ctx* c) {
   if (!c) return -1;
+  DeviceGuard dev_guard(c->device);
   for (auto& kvp : c->slots)
     if (!kvp.second.loaded && !kvp.second.optional) return fail(c, "weight not loaded: %s", kvp.first.c_str());
   return 0;
@@ -1156,6 +1185,7 @@ int ccb_preprocess_image(ccb_ctx* c, const uint8_t* rgb_hwc, int H, int W, int n
                          int n_px, const float* mean3, const float* std3, float* out_chw, void* scratch, int64_t scratch_bytes,
                          void* stream) {
   if (!c || !rgb_hwc || !mean3 || !std3 || !out_chw || !scratch) return fail(c, "ccb_preprocess_image: null argument");
+  DeviceGuard dev_guard(c->device);
   const int r = preprocess_image(rgb_hwc, H, W, new_h, new_w, crop_top, crop_left, n_px, mean3, std3, out_chw, scratch,
                                  static_cast<size_t>(scratch_bytes), static_cast<cudaStream_t>(stream));
   if (r != 0) return fail(c, "ccb_preprocess_image: bad geometry / scratch too small / launch failed (%d)", r);
@@ -1165,37 +1195,45 @@ int ccb_preprocess_image(ccb_ctx* c, const uint8_t* rgb_hwc, int H, int W, int n
 
 int ccb_vit_encode(ccb_ctx* c, const void* images, int dtype, int B, float* feat_out, void* stream) {
   if (!c || !images || !feat_out) return fail(c, "ccb_vit_encode: null argument");
+  DeviceGuard dev_guard(c->device);
   return vit_forward(c, images, dtype, B, feat_out, static_cast<cudaStream_t>(stream));
 }
 
 int ccb_vit_encode_tokens(ccb_ctx* c, const void* images, int dtype, int B, float* tokens_out, void* stream) {
   if (!c || !images || !tokens_out) return fail(c, "ccb_vit_encode_tokens: null argument");
+  DeviceGuard dev_guard(c->device);
   return vit_forward(c, images, dtype, B, tokens_out, static_cast<cudaStream_t>(stream), true);
 }
 
 int ccb_clip_encode_text(ccb_ctx* c, const int32_t* tokens, int B, float* feat_out, void* stream) {
   if (!c || !tokens || !feat_out) return fail(c, "ccb_clip_encode_text: null argument");
+  DeviceGuard dev_guard(c->device);
   return text_forward(c, tokens, B, feat_out, static_cast<cudaStream_t>(stream));
 }
 
 int ccb_map_prefix(ccb_ctx* c, const float* feat, int B, float* prefix_out, void* stream) {
   if (!c || !feat || !prefix_out) return fail(c, "ccb_map_prefix: null argument");
+  DeviceGuard dev_guard(c->device);
   return map_forward(c, feat, B, prefix_out, c->desc.map_prefix_len, static_cast<cudaStream_t>(stream));
 }
 
 int ccb_embed_tokens(ccb_ctx* c, const int32_t* tokens, int n, float* out, void* stream) {
   if (!c || !tokens || !out) return fail(c, "ccb_embed_tokens: null argument");
+  DeviceGuard dev_guard(c->device);
   if (n <= 0) return 0;
-  RUN(embed_tokens(c->wte, nullptr, tokens, nullptr, out, n, c->desc.lm_d, static_cast<cudaStream_t>(stream)));
+  RUN(embed_tokens(c->wte, nullptr, tokens, nullptr, out, n, c->desc.lm_d, c->desc.lm_vocab, 1, static_cast<cudaStream_t>(stream)));
   return 0;
 }
 
 int ccb_lm_forward(ccb_ctx* c, const float* embeds, int B, int S, const uint8_t* key_mask, float* logits_out,
                    int64_t ld_logits, int last_only, void* stream) {
   if (!c || !embeds || !logits_out) return fail(c, "ccb_lm_forward: null argument");
+  DeviceGuard dev_guard(c->device);
   if (B <= 0 || S <= 0 || static_cast<long long>(B) * S > c->desc.max_lm_tokens)
     return fail(c, "ccb_lm_forward: B*S=%lld exceeds max_lm_tokens=%d", static_cast<long long>(B) * S, c->desc.max_lm_tokens);
   if (S > 256) return fail(c, "ccb_lm_forward: S=%d > 256 is not supported", S);
+  if (c->desc.lm_arch == CCB_LM_GPT2 && S > c->desc.lm_n_pos)
+    return fail(c, "ccb_lm_forward: S=%d exceeds the model's %d learned positions", S, c->desc.lm_n_pos);
   if (ld_logits < c->desc.lm_vocab) return fail(c, "ccb_lm_forward: ld_logits < vocab");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (lm_prefill_layers(c, embeds, B, S, key_mask, false, s)) return -1;
@@ -1205,6 +1243,7 @@ int ccb_lm_forward(ccb_ctx* c, const float* embeds, int B, int S, const uint8_t*
 int ccb_generate(ccb_ctx* c, const ccb_gen_params* p, const float* embeds, int N, int S0, int32_t* tokens_out,
                  int32_t* lengths_out, float* scores_out, void* stream) {
   if (!c || !p || !embeds || !tokens_out) return fail(c, "ccb_generate: null argument");
+  DeviceGuard dev_guard(c->device);
   cudaStream_t caller = static_cast<cudaStream_t>(stream);
   if (fence_in(c, caller)) return -1;
   const int r = generate_on_work_stream(c, p, embeds, N, S0, tokens_out, lengths_out, scores_out);
@@ -1215,6 +1254,7 @@ int ccb_generate(ccb_ctx* c, const ccb_gen_params* p, const float* embeds, int N
 int ccb_caption_images(ccb_ctx* c, const ccb_gen_params* p, const void* images, int dtype, int N, int append_bos,
                        int32_t* tokens_out, int32_t* lengths_out, float* scores_out, void* stream) {
   if (!c || !p || !images || !tokens_out) return fail(c, "ccb_caption_images: null argument");
+  DeviceGuard dev_guard(c->device);
   cudaStream_t caller = static_cast<cudaStream_t>(stream);
   if (fence_in(c, caller)) return -1;
   cudaStream_t s = c->work;
@@ -1242,6 +1282,7 @@ int ccb_caption_images(ccb_ctx* c, const ccb_gen_params* p, const void* images, 
 
 int ccb_timing_sum(ccb_ctx* c, int n_calls, float* prefill_ms, float* decode_ms, int* decode_steps) {
   if (!c) return -1;
+  DeviceGuard dev_guard(c->device);
   if (n_calls <= 0 || n_calls > ccb_ctx::kTimingSlots || n_calls > c->generate_calls)
     return fail(c, "ccb_timing_sum: n_calls=%d outside [1, min(%d, generate calls so far = %lld)]", n_calls,
                 ccb_ctx::kTimingSlots, c->generate_calls);
@@ -1263,6 +1304,8 @@ int ccb_timing_sum(ccb_ctx* c, int n_calls, float* prefill_ms, float* decode_ms,
 }
 
 int ccb_last_timing(ccb_ctx* c, float* prefill_ms, float* decode_ms, int* decode_steps) {
+  if (!c) return -1;
+  DeviceGuard dev_guard(c->device);
   return ccb_timing_sum(c, 1, prefill_ms, decode_ms, decode_steps);
 }
 
@@ -1271,6 +1314,7 @@ int ccb_sample(ccb_ctx* c, const float* logits, int64_t ld, int B, int V, const 
                const int32_t* history, int64_t ld_hist, int hist_len, int step, float* filtered_out, int32_t* next_out,
                int32_t* alt_out, void* stream) {
   if (!c || !logits || !p || !next_out) return fail(c, "ccb_sample: null argument");
+  DeviceGuard dev_guard(c->device);
   SampleParams sp = sample_params(c, p, B);
   sp.history = history;
   sp.ld_hist = ld_hist;
@@ -1285,6 +1329,7 @@ int ccb_sample(ccb_ctx* c, const float* logits, int64_t ld, int B, int V, const 
 
 int ccb_argmax(ccb_ctx* c, const float* logits, int64_t ld, int B, int V, int32_t* next_out, void* stream) {
   if (!c || !logits || !next_out) return fail(c, "ccb_argmax: null argument");
+  DeviceGuard dev_guard(c->device);
   RUN(sample_greedy(logits, ld, B, V, next_out, static_cast<cudaStream_t>(stream)));
   return 0;
 }
@@ -1292,6 +1337,7 @@ int ccb_argmax(ccb_ctx* c, const float* logits, int64_t ld, int B, int V, int32_
 int ccb_cross_entropy(ccb_ctx* c, const float* logits, int64_t ld, int rows, int V, const int32_t* targets,
                       const int32_t* row_map, int ignore_index, float* row_loss, float* loss_out, void* stream) {
   if (!c || !logits || !targets || !row_loss || !loss_out) return fail(c, "ccb_cross_entropy: null argument");
+  DeviceGuard dev_guard(c->device);
   if (rows <= 0 || V <= 0 || ld < V) return fail(c, "ccb_cross_entropy: rows=%d V=%d ld=%lld", rows, V, static_cast<long long>(ld));
   RUN(cross_entropy(logits, ld, rows, V, targets, row_map, ignore_index, row_loss, loss_out, static_cast<cudaStream_t>(stream)));
   c->launches++;   // (two kernels)
@@ -1303,6 +1349,7 @@ int ccb_beam_step(ccb_ctx* c, const float* logits, int64_t ld, int N, int beam, 
                   int max_len, int32_t* next_tokens, int32_t* src_rows, void* stream) {
   if (!c || !logits || !scores || !seq_lengths || !has_stopped || !tokens || !next_tokens || !src_rows)
     return fail(c, "ccb_beam_step: null argument");
+  DeviceGuard dev_guard(c->device);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   // the step counter lives in device memory for the graph-replayed loop; stage the caller's value
   CUDA_OK(cudaMemcpyAsync(c->step, &step, sizeof(int), cudaMemcpyHostToDevice, s));
@@ -1323,6 +1370,7 @@ int ccb_op_linear(ccb_ctx* c, const void* x, int64_t lda, int tokens, const void
                   const float* bias, int act, const float* residual, int64_t ldr, void* out, int64_t ldo, int out_bf16,
                   int orientation, int bn, int split_k, void* stream) {
   if (!c || !x || !w || !out) return fail(c, "ccb_op_linear: null argument");
+  DeviceGuard dev_guard(c->device);
   GemmArgs g;
   g.act = static_cast<const bf16*>(x);
   g.lda = lda;
@@ -1363,6 +1411,7 @@ int ccb_debug_set_mega(ccb_ctx* c, int enable) {
 
 int ccb_debug_copy_buffer(ccb_ctx* c, int which, void* dst, int64_t bytes, void* stream) {
   if (!c || !dst) return -1;
+  DeviceGuard dev_guard(c->device);
   const void* src = nullptr;
   switch (which) {
     case 0: src = c->h; break;
@@ -1395,6 +1444,7 @@ int ccb_debug_mega_trace(ccb_ctx* c, void* trace_u64) {
 int ccb_op_layernorm(ccb_ctx* c, const float* x, const float* gamma, const float* beta, float eps, void* y_bf16,
                      int rows, int d, void* stream) {
   if (!c || !x || !gamma || !beta || !y_bf16) return fail(c, "ccb_op_layernorm: null argument");
+  DeviceGuard dev_guard(c->device);
   RUN(layernorm_f32_bf16(x, d, gamma, beta, eps, static_cast<bf16*>(y_bf16), d, rows, d, static_cast<cudaStream_t>(stream)));
   return 0;
 }
@@ -1402,6 +1452,7 @@ int ccb_op_layernorm(ccb_ctx* c, const float* x, const float* gamma, const float
 int ccb_op_attention(ccb_ctx* c, const void* qkv_bf16, void* out_bf16, int B, int S, int H, int hd, float scale,
                      int causal, int rotary_dim, void* stream) {
   if (!c || !qkv_bf16 || !out_bf16) return fail(c, "ccb_op_attention: null argument");
+  DeviceGuard dev_guard(c->device);
   RUN(attention_prefill(static_cast<const bf16*>(qkv_bf16), static_cast<bf16*>(out_bf16), B, S, H, hd, scale, causal,
                         nullptr, 0, nullptr, 0, rotary_dim, nullptr, static_cast<cudaStream_t>(stream)));
   return 0;

@@ -20,7 +20,6 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode = nullptr;
 char g_err[512] = {0};
-std::once_flag g_attr_once;
 int g_attr_status = 0;
 
 int fail(const char* fmt, const char* detail = "") {
@@ -207,7 +206,13 @@ int gemm_init(int device) {
       return fail("cuTensorMapEncodeTiled not available from the driver: %s", cudaGetErrorString(e));
     g_encode = reinterpret_cast<EncodeTiledFn>(fn);
   }
-  std::call_once(g_attr_once, [] {
+  // function attributes are per device: once per device of this process (gemm_init runs under ccb_create's device)
+  static std::mutex mu;
+  static int status_dev[kMaxDevices];
+  static bool done_dev[kMaxDevices] = {};
+  std::lock_guard<std::mutex> lock(mu);
+  const int slot = current_device_slot();
+  if (!done_dev[slot]) {
     int r = 0;
     r |= set_attr<32>();
     r |= set_attr<64>();
@@ -216,9 +221,10 @@ int gemm_init(int device) {
     if (cudaFuncSetAttribute(gemm_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPersistSmemBytes) != cudaSuccess ||
         cudaFuncSetAttribute(gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPersistSmemBytes) != cudaSuccess)
       r |= fail("cudaFuncSetAttribute(smem) failed for the persistent GEMM");
-    g_attr_status = r;
-  });
-  return g_attr_status;
+    status_dev[slot] = r;
+    done_dev[slot] = true;
+  }
+  return status_dev[slot];
 }
 
 int gemm_launch(const GemmArgs& a, const GemmWorkspace& w, cudaStream_t stream) {

@@ -10,6 +10,15 @@ namespace ccb {
 
 typedef __nv_bfloat16 bf16;
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per DEVICE: "already configured" state is kept per device so that a
+// second context on another GPU of the same process configures its kernels too.
+constexpr int kMaxDevices = 64;
+inline int current_device_slot() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return d >= 0 && d < kMaxDevices ? d : 0;
+}
+
 // Programmatic dependent launch for the kernels of the decode chain (they all call ptx::grid_dep_wait() before
 // touching activations): CCB_PDL=0 in the environment switches it off.
 bool pdl_enabled();
@@ -93,9 +102,11 @@ int mapper_fill_const(const float* prefix_const, float* seq, int B, int clip_len
 int mapper_fill_pos(const float* pos, float* seq, int B, int clip_len, int P, int d, cudaStream_t s);
 // f32 -> bf16 cast of a [rows, d] block (leading dims in elements)
 int cast_f32_bf16(const float* x, long long ldx, bf16* y, long long ldy, int rows, int d, cudaStream_t s);
+// geglu (layers/Transformer.py:112-114) in place: x[r, j] = x[r, j] * gelu(x[r, h + j]) for j < h, rows of pitch ldx >= 2h
+int geglu_inplace(bf16* x, long long ldx, int rows, int h, cudaStream_t s);
 // bf16/f32 embedding gather: h[r, :] = table[tok[r], :] (+ wpe[pos[r], :] if wpe) -> f32 [rows, d]
 int embed_tokens(const bf16* wte, const bf16* wpe, const int* tokens, const int* positions, float* h, int rows, int d,
-                 cudaStream_t s);
+                 int vocab, int n_pos, cudaStream_t s);
 // h[r,:] = src[r,:] (f32) + wpe[pos0 + r % S, :]   -- prefill of externally supplied embeddings
 int add_positions(const float* src, const bf16* wpe, int pos0, int S, float* h, int rows, int d, cudaStream_t s);
 // copy rows of a strided f32 block: dst[r, :] = src[(r / gi) * go + off + r % gi, :]

@@ -248,13 +248,15 @@ __global__ void __launch_bounds__(256) cast_kernel(const float* __restrict__ x, 
 
 __global__ void __launch_bounds__(256) embed_kernel(const bf16* __restrict__ wte, const bf16* __restrict__ wpe,
                                                     const int* __restrict__ tokens, const int* __restrict__ positions,
-                                                    float* __restrict__ h, int d) {
+                                                    float* __restrict__ h, int d, int vocab, int n_pos) {
   ptx::grid_dep_wait();
   ptx::grid_dep_launch();
   const int r = blockIdx.x;
-  const int tok = tokens[r];
+  // ids are range-checked by the host side (torch raises IndexError there); the clamp keeps a bad id handed to the C ABI
+  // from becoming an illegal address that would poison the context
+  const int tok = min(max(tokens[r], 0), vocab - 1);
   const uint2* te = reinterpret_cast<const uint2*>(wte + static_cast<long long>(tok) * d);
-  const uint2* pe = wpe ? reinterpret_cast<const uint2*>(wpe + static_cast<long long>(positions[r]) * d) : nullptr;
+  const uint2* pe = wpe ? reinterpret_cast<const uint2*>(wpe + static_cast<long long>(min(max(positions[r], 0), n_pos - 1)) * d) : nullptr;
   float4* hr = reinterpret_cast<float4*>(h + static_cast<long long>(r) * d);
   for (int c = threadIdx.x; c < d / 4; c += blockDim.x) {
     const uint2 a = __ldg(te + c);
@@ -418,6 +420,30 @@ int mapper_fill_pos(const float* pos, float* seq, int B, int clip_len, int P, in
   return 0;
 }
 
+// x, gate = chunk(2, -1); x * gelu(gate) with the erf form of nnf.gelu; one CTA per row, 8 bf16 per access
+__global__ void geglu_kernel(bf16* __restrict__ x, long long ldx, int h) {
+  bf16* row = x + static_cast<long long>(blockIdx.x) * ldx;
+  for (int j = threadIdx.x * 8; j < h; j += blockDim.x * 8) {
+    const uint4 a = *reinterpret_cast<const uint4*>(row + j), g = *reinterpret_cast<const uint4*>(row + h + j);
+    const uint32_t av[4] = {a.x, a.y, a.z, a.w}, gv[4] = {g.x, g.y, g.z, g.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 xa = unpack_bf16x2(av[k]), xg = unpack_bf16x2(gv[k]);
+      o[k] = pack_bf16x2(xa.x * apply_act(xg.x, ACT_GELU_ERF), xa.y * apply_act(xg.y, ACT_GELU_ERF));
+    }
+    *reinterpret_cast<uint4*>(row + j) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+int geglu_inplace(bf16* x, long long ldx, int rows, int h, cudaStream_t s) {
+  if (rows <= 0) return 0;
+  if (h % 8 || ldx % 8) return (int)cudaErrorInvalidValue;
+  geglu_kernel<<<rows, 256, 0, s>>>(x, ldx, h);
+  CCB_LAUNCH_CHECK();
+  return 0;
+}
+
 int cast_f32_bf16(const float* x, long long ldx, bf16* y, long long ldy, int rows, int d, cudaStream_t s) {
   if (rows <= 0) return 0;
   if (d % 4 || ldx % 4 || ldy % 4) return (int)cudaErrorInvalidValue;
@@ -427,11 +453,11 @@ int cast_f32_bf16(const float* x, long long ldx, bf16* y, long long ldy, int row
 }
 
 int embed_tokens(const bf16* wte, const bf16* wpe, const int* tokens, const int* positions, float* h, int rows, int d,
-                 cudaStream_t s) {
+                 int vocab, int n_pos, cudaStream_t s) {
   if (rows <= 0) return 0;
   if (d % 4) return (int)cudaErrorInvalidValue;
   {
-    cudaError_t e = launch_kernel(embed_kernel, dim3(rows), dim3(256), 0, s, true, wte, wpe, tokens, positions, h, d);
+    cudaError_t e = launch_kernel(embed_kernel, dim3(rows), dim3(256), 0, s, true, wte, wpe, tokens, positions, h, d, vocab, n_pos);
     if (e != cudaSuccess) return (int)e;
   }
   return 0;

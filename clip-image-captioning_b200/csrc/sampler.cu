@@ -836,7 +836,8 @@ int sample_top_p(const float* logits, long long ld, int B, int V, const SamplePa
   if (B <= 0) return 0;
   const size_t smem = static_cast<size_t>(V) * sizeof(float);
   if (smem > 208 * 1024) return (int)cudaErrorInvalidValue;
-  static bool configured = false;
+  static bool configured_dev[kMaxDevices] = {};
+  bool& configured = configured_dev[current_device_slot()];
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(top_p_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
     if (e != cudaSuccess) return (int)e;
@@ -870,7 +871,8 @@ int beam_step(const float* logits, long long ld, int N, int beam, int V, float t
   const int m = st.max_len > max_pages ? st.max_len : max_pages;
   const size_t smem = static_cast<size_t>(beam) * m * sizeof(int);
   if (smem > 64 * 1024) return (int)cudaErrorInvalidValue;
-  static bool configured = false;
+  static bool configured_dev[kMaxDevices] = {};
+  bool& configured = configured_dev[current_device_slot()];
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(beam_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     if (e != cudaSuccess) return (int)e;

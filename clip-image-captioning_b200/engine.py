@@ -246,6 +246,7 @@ class Engine:
         tk = self._dev(tokens, torch.int32)
         if tk.dim() != 2 or tk.shape[1] != self.cfg.text_ctx:
             raise ValueError("tokens must be [B, %d]" % self.cfg.text_ctx)
+        self._check_ids(tk, self.cfg.text_vocab, "clip_encode_text")
         out = torch.empty(tk.shape[0], self.cfg.text_out, device=self.device, dtype=torch.float32)
         self._check(self.lib.ccb_clip_encode_text(self._h, _ptr(tk), tk.shape[0], _ptr(out), self._stream()))
         return out
@@ -262,7 +263,20 @@ class Engine:
         self._check(self.lib.ccb_map_prefix(self._h, _ptr(feat), B, _ptr(out), self._stream()))
         return out
 
+    @staticmethod
+    def _check_ids(ids: torch.Tensor, n: int, what: str, also_ok: Optional[int] = None):
+        """torch's embedding / cross_entropy raise on ids outside [0, n): same here (the reference dataset pads with -1,
+        model.py:204 masks those before the lookup; the kernels clamp rather than fault)."""
+        if ids.numel() == 0:
+            return
+        bad = (ids < 0) | (ids >= n)
+        if also_ok is not None:
+            bad &= ids != also_ok
+        if bool(bad.any()):
+            raise IndexError("%s: id out of range [0, %d): %d" % (what, n, int(ids[bad].flatten()[0])))
+
     def embed_tokens(self, tokens: torch.Tensor) -> torch.Tensor:
+        self._check_ids(tokens, self.cfg.lm_vocab, "embed_tokens")
         tk = self._dev(tokens, torch.int32)
         out = torch.empty(*tk.shape, self.cfg.lm_d, device=self.device, dtype=torch.float32)
         if tk.numel():
@@ -307,6 +321,14 @@ class Engine:
             keep.append(row_ids)
         if top_p_rows is not None:
             top_p_rows = self._dev(top_p_rows, torch.float32)
+            # sampling.py:149-160: with a tensor of budgets the nucleus filter runs on EVERY row as soon as one budget is
+            # positive, and a row whose budget is <= 0 then keeps its top-1 token only (cumsum > top_p holds everywhere);
+            # the kernel skips rows with a budget <= 0, so those get the smallest positive budget instead
+            if bool((top_p_rows > 0).any()):
+                top_p_rows = torch.where(top_p_rows > 0, top_p_rows, torch.full_like(top_p_rows, 1e-30))
+            else:
+                top_p_rows = None
+        if top_p_rows is not None:
             p.top_p_rows = top_p_rows.data_ptr()
             keep.append(top_p_rows)
         if top_k_rows is not None:
@@ -417,9 +439,10 @@ class Engine:
         (loss 0-d tensor, per-row loss [rows], number of counted rows 0-d tensor)."""
         if logits.dim() != 2 or logits.stride(1) != 1:
             raise ValueError("cross_entropy: logits must be [n, V] with unit stride along V")
-        logits = self._dev(logits, torch.float32)
+        logits = logits.to(self.device, dtype=torch.float32)      # (rows may be strided: the pitch goes to the kernel, no copy)
         tg = self._dev(targets).to(torch.int32).contiguous().view(-1)
         rows, V = tg.numel(), logits.shape[1]
+        self._check_ids(tg, V, "cross_entropy targets", also_ok=ignore_index)
         rm = None
         if row_map is not None:
             rm = self._dev(row_map).to(torch.int32).contiguous().view(-1)

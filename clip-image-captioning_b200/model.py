@@ -117,6 +117,12 @@ class CLIPCaptionModel:
                 kw["map_clip_len"] = state_dict["clip_project.pos_embeddings"].shape[0]
             elif kw.get("vit"):
                 kw["map_clip_len"] = (kw["vit_image"] // kw["vit_patch"]) ** 2 + 1
+        # capacities the reference-signature defaults need: generate_beam(beam_size=5, entry_length=67), generate_no_beam (nine
+        # captions per image, entry_length=67), evaluate_model.generate_no_beam (BOS + max_decode_length <= 77)
+        kw.setdefault("max_beam", 5)
+        n_pos = kw.get("lm_n_pos", EngineConfig.lm_n_pos)
+        want_ctx = kw.get("map_prefix_len", EngineConfig.map_prefix_len) + 1 + 77
+        kw.setdefault("max_ctx", min(want_ctx, n_pos) if kw.get("lm_arch", "gpt2") == "gpt2" else want_ctx)
         kw.update(overrides)
         fields = set(EngineConfig.__dataclass_fields__)
         unknown = set(kw) - fields

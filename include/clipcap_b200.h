@@ -39,7 +39,8 @@ enum { CCB_MAP_NONE = 0, CCB_MAP_TRANSFORMER = 1, CCB_MAP_MLP = 2, CCB_MAP_TRANS
 /* activation codes (mapper act_fn_name, layers/Transformer.py:117-130; ViT QuickGELU; GPT gelu_new) */
 enum {
   CCB_ACT_NONE = 0, CCB_ACT_RELU = 1, CCB_ACT_QUICKGELU = 2, CCB_ACT_GELU_NEW = 3, CCB_ACT_GELU = 4,
-  CCB_ACT_ELU = 5, CCB_ACT_SELU = 6, CCB_ACT_TANH = 7
+  CCB_ACT_ELU = 5, CCB_ACT_SELU = 6, CCB_ACT_TANH = 7,
+  CCB_ACT_GEGLU = 8   /* mapper MLP only (layers/Transformer.py:74,112-114): fc1 is 2 x hidden wide, x * gelu(gate) */
 };
 enum { CCB_GEN_GREEDY = 0, CCB_GEN_SAMPLE = 1, CCB_GEN_BEAM = 2 };
 

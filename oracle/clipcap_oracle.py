@@ -31,7 +31,13 @@ def gelu_new(x):  # HF activations.NewGELUActivation (GPT-2 / GPT-J "gelu_new")
     return 0.5 * x * (1.0 + torch.tanh(math.sqrt(2.0 / math.pi) * (x + 0.044715 * torch.pow(x, 3.0))))
 
 
-ACTS = {"relu": F.relu, "elu": F.elu, "gelu": F.gelu, "selu": F.selu}  # layers/Transformer.py:117-130
+def geglu(x):
+    """layers/Transformer.py:112-114 (fc1 is then 2 x hidden wide, :74)."""
+    x, gate = x.chunk(2, dim=-1)
+    return x * F.gelu(gate)
+
+
+ACTS = {"relu": F.relu, "elu": F.elu, "gelu": F.gelu, "selu": F.selu, "geglu": geglu}  # layers/Transformer.py:117-130
 
 
 # ------------------------------------------------------------------------------------------------ ViT

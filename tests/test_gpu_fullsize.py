@@ -56,6 +56,9 @@ def test_cached_decode_agrees_with_teacher_forced_forward(xl):
         margin = (lg.max() - lg[tokens[r, t]]).item()
         scale = (lg.max() - lg.min()).item()
         assert margin <= 2e-2 * scale, (r, t, margin, scale)
+    # every row is identical under the tie rule (asserted above: tests/test_gpu_config_parity.py states the rule); strictly,
+    # >= 99 % of the individual decisions agree, and a free-running row survives without any near-tie flip 3 times out of 4
+    assert agree.float().mean().item() >= 0.99 - 1e-9 or (~agree).sum().item() <= 2, agree.float().mean().item()
     first_flip_free = sum(int(agree[r].all()) for r in range(tokens.shape[0]))
     assert first_flip_free >= 0.75 * tokens.shape[0], first_flip_free
     assert agree[:, 0].float().mean().item() >= 0.99          # the first token comes from the same prefill in both

@@ -88,7 +88,7 @@ def test_gpt2_xl_against_transformers_fp32(full):
     for r, t in bad.tolist():
         margin = (pred[r, t].max() - pred[r, t, tokens[r, t]]).item()
         assert margin <= TOL * scale, (r, t, margin, scale)   # only near-ties may differ
-    assert frac >= 0.97, frac
+    assert frac >= 0.99, frac        # (per-image numbers at 256 images x 32 tokens: tests/test_gpu_config_parity.py)
     print("greedy tokens identical to transformers fp32 at %.2f %% of %d positions" % (100 * frac, agree.numel()))
 
 

@@ -44,6 +44,14 @@ def test_mapper_matches_reference(fx):
     assert close(prefix, fx["prefix"])
 
 
+@pytest.mark.parametrize("act", ["elu", "gelu", "selu", "geglu"])
+def test_mapper_activations_match_reference(act):
+    """parse_act_fn's other activations (layers/Transformer.py:117-130), geglu with its 2 x hidden fc1 (:74, :112-114)."""
+    ax = load("tiny_mapper_acts.pt")
+    prefix = orc.mapper_forward(f32(ax["sd_" + act]), ax["feat"], ax["CL"], ax["map_heads"], act)
+    assert close(prefix, ax["prefix_" + act])
+
+
 def test_lm_call_matches_reference(fx):
     assert close(fx["lm"].logits(fx["prefix"]), fx["logits_prefix"], 5e-5)
 

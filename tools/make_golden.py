@@ -291,6 +291,22 @@ def make_allfeatures_fixture(ref, seed):
     return fx
 
 
+def make_mapper_acts_fixture(ref, seed):
+    """layers.TransformerMapper (layers/Transformer.py:133-161) of the UNMODIFIED reference with every activation
+    parse_act_fn accepts besides relu (:117-130): elu, gelu, selu and geglu (fc1 twice as wide, :74, :112-114)."""
+    fx = {"dim_clip": 64, "d": 128, "P": 4, "CL": 4, "map_heads": 8}
+    torch.manual_seed(seed)
+    fx["feat"] = torch.randn(3, 64)
+    for act in ("elu", "gelu", "selu", "geglu"):
+        m = ref.layers.TransformerMapper(dim_clip=64, dim_embedding=128, prefix_length=4, clip_length=4, num_heads=8, num_layers=2,
+                                         mlp_ratio=4.0, prefix_init_std=1.0, act_fn_name=act)
+        bf16_round_(m).eval()
+        with torch.no_grad():
+            fx["prefix_" + act] = m(fx["feat"])
+        fx["sd_" + act] = pack_sd(m.state_dict())
+    return fx
+
+
 def export_clip_text(hf):
     """HF CLIPTextModelWithProjection -> OpenAI CLIP text-tower names (token_embedding, positional_embedding,
     transformer.resblocks.N.*, ln_final, text_projection)."""
@@ -409,6 +425,12 @@ def make_loss_fixture():
 def main():
     ref = ref_harness.load_reference()
     os.makedirs(OUT, exist_ok=True)
+    if "--acts" in sys.argv:
+        fx = make_mapper_acts_fixture(ref, 26)
+        path = os.path.join(OUT, "tiny_mapper_acts.pt")
+        torch.save(fx, path)
+        print(path, os.path.getsize(path) // 1024, "KiB", {k: tuple(v.shape) for k, v in fx.items() if k.startswith("prefix_")})
+        return
     if "--loss" in sys.argv:
         fx = make_loss_fixture()
         path = os.path.join(OUT, "tiny_loss.pt")
