@@ -505,6 +505,47 @@ def generate_no_beam(lm: OracleLM, embeds: torch.Tensor, top_p_values: Sequence[
     return out
 
 
+def generate_clip_guided(lm: OracleLM, embeds: torch.Tensor, image_embedding: torch.Tensor, tokenize_fn, encode_text_fn,
+                         bos_token: int, special_ids: Sequence[int], max_decode_length: int = 75,
+                         repetition_penalty: float = 1.2, look_ahead: int = 5, branching_factor: int = 3) -> List[int]:
+    """evaluate_model.py:182-312 for ONE image (`greedy = True`, step_by_step=False: the other branch reads an undefined
+    name): BOS after the prefix (:249-258), then rounds of a depth-first tree search -- at every node the `branching_factor`
+    largest (repetition-penalised, :213-216) logits, depth min(look_ahead, room left) (:268), a special id ends a branch
+    (:243-245) -- whose leaves are scored by CLIP: decode -> clip.tokenize -> encode_text -> cosine similarity with the
+    image embedding (:276-285); the best leaf's tokens are accepted whole (:303).  `tokenize_fn(list of token lists)` and
+    `encode_text_fn(clip tokens)` stand for `clip.tokenize(tokenizer.decode_tokens(..))` / `clip_model.encode_text`
+    (neither BPE vocabulary exists offline).  Returns the token ids without the special ones (:310)."""
+    if image_embedding.dim() == 3 and image_embedding.shape[-2] > 1:
+        image_embedding = image_embedding[:, 0, :]
+    embeds = torch.cat((embeds, lm.get_embedding_text(torch.full((1, 1), bos_token, dtype=torch.int64))), dim=1)
+    tokens: List[int] = []
+
+    def branch(cands, emb, toks, depth):
+        logits = lm.logits(emb)[0, -1, :]
+        if repetition_penalty != 1.0 and toks:
+            logits = repetition_penalty_apply(logits, torch.tensor(toks, dtype=torch.int64), repetition_penalty)
+        for t in logits.topk(branching_factor).indices.tolist():
+            nt = toks + [t]
+            ne = torch.cat((emb, lm.get_embedding_text(torch.tensor([[t]], dtype=torch.int64))), dim=1)
+            stop = t in special_ids
+            if depth == 0 or stop:
+                cands.append((nt, ne, stop))
+            else:
+                branch(cands, ne, nt, depth - 1)
+
+    while True:
+        cands = []
+        branch(cands, embeds, tokens, min(look_ahead, max_decode_length - len(tokens)))
+        feats = encode_text_fn(tokenize_fn([c[0] for c in cands])).float()
+        img = image_embedding / torch.norm(image_embedding)
+        feats = feats / torch.norm(feats, dim=-1, keepdim=True)
+        best = int((img @ feats.T).argmax())
+        tokens, embeds, stop = cands[best]
+        if stop or len(tokens) >= max_decode_length:
+            break
+    return [t for t in tokens if t not in special_ids]
+
+
 def generate_greedy(lm: OracleLM, embeds: torch.Tensor, entry_length: int, stop_token: int = 13,
                     use_cache: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
     """Batched greedy = generate_beam(beam_size=1) applied per row (batched generation is the

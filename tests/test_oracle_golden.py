@@ -111,6 +111,32 @@ def test_generate_no_beam_evaluate_matches_reference(fx):
         assert got == want
 
 
+def clip_tokenize_ids(texts, ctx, sot, eot):
+    """tools/make_golden.py's stand-in for clip.tokenize on id lists: [sot] + ids + [eot], truncated, zero-padded."""
+    out = torch.zeros(len(texts), ctx, dtype=torch.int64)
+    for i, t in enumerate(texts):
+        ids = [sot] + [int(x) for x in t] + [eot]
+        if len(ids) > ctx:
+            ids = ids[:ctx]
+            ids[-1] = eot
+        out[i, :len(ids)] = torch.tensor(ids)
+    return out
+
+
+def test_generate_clip_guided_matches_reference():
+    """evaluate_model.generate_clip_guided (:182-312) of the unmodified reference vs the oracle's restatement."""
+    base, gx = load("tiny_gpt2.pt"), load("tiny_clip_guided.pt")
+    lm = orc.OracleLM(f32(base["sd_lm"]), "gpt2", base["heads"], 0)
+    sd_text = f32(gx["sd_text"])
+    tokenize = lambda texts: clip_tokenize_ids(texts, gx["ctx"], gx["sot"], gx["eot"])
+    encode = lambda tok: orc.clip_text_forward(sd_text, tok, gx["heads"])
+    V = base["V"]
+    for run in gx["runs"]:
+        for i, want in enumerate(run["captions"]):
+            got = orc.generate_clip_guided(lm, base["prefix"][i:i + 1], base["feat"][i:i + 1], tokenize, encode, V - 1, [V - 1], **run["kw"])
+            assert got == want, (run["kw"], i, got, want)
+
+
 def test_greedy_batched_equals_per_image(fx):
     toks, lens = orc.generate_greedy(fx["lm"], fx["prefix"], 10, fx["stop_id"])
     for i, want in enumerate(fx["greedy"]):

@@ -307,6 +307,61 @@ def make_mapper_acts_fixture(ref, seed):
     return fx
 
 
+def clip_tokenize_ids(texts, ctx, sot, eot):
+    """Stand-in for clip.tokenize(texts, truncate=True) on `texts` that are lists of token ids (TokenizerStub.decode_tokens):
+    [sot] + ids + [eot], truncated to `ctx` with the end-of-text id kept last, zero-padded -- clip.tokenize's own layout."""
+    out = torch.zeros(len(texts), ctx, dtype=torch.int64)
+    for i, t in enumerate(texts):
+        ids = [sot] + [int(x) for x in (t if isinstance(t, (list, tuple)) else [t])] + [eot]
+        if len(ids) > ctx:
+            ids = ids[:ctx]
+            ids[-1] = eot
+        out[i, :len(ids)] = torch.tensor(ids)
+    return out
+
+
+def make_clip_guided_fixture(ref, seed):
+    """evaluate_model.generate_clip_guided (evaluate_model.py:182-312) of the UNMODIFIED reference on the tiny GPT-2 fixture's
+    language model, prefixes and image embeddings, with a tiny CLIP text tower (HF CLIPTextModelWithProjection, arg-max
+    pooling = OpenAI's rule) as `clip_model.encode_text` and `clip.tokenize` replaced by `clip_tokenize_ids`."""
+    from transformers import CLIPTextConfig, CLIPTextModelWithProjection, GPT2Config
+    base = torch.load(os.path.join(OUT, "tiny_gpt2.pt"), weights_only=False)
+    torch.manual_seed(seed)
+    V, d = base["V"], base["d"]
+    lm = ref.lms.GPT2(GPT2Config(vocab_size=V, n_positions=64, n_embd=d, n_layer=2, n_head=base["heads"]))
+    lm.load_state_dict({k: v.float() for k, v in base["sd_lm"].items()}, strict=False)
+    lm.tie_weights()
+    lm.eval()
+    Vc, ctx, w, heads, out = V + 2, 24, 64, 2, base["dim_clip"]
+    cfg = CLIPTextConfig(vocab_size=Vc, hidden_size=w, intermediate_size=4 * w, num_hidden_layers=2, num_attention_heads=heads,
+                         max_position_embeddings=ctx, projection_dim=out, hidden_act="quick_gelu", eos_token_id=2,
+                         bos_token_id=0, pad_token_id=1)
+    m = bf16_round_(CLIPTextModelWithProjection(cfg).eval())
+    with torch.no_grad():
+        for n_, p_ in m.named_parameters():
+            if p_.dim() == 2 and "embedding" not in n_:
+                p_.mul_(4.0)
+    m = bf16_round_(m)
+    sot, eot = Vc - 2, Vc - 1
+
+    class ClipModel:
+        def encode_text(self, tokens):
+            with torch.no_grad():
+                return m(input_ids=tokens).text_embeds
+
+    tok = TokenizerStub(base["stop_id"], bos=V - 1, special=[V - 1])
+    model = types.SimpleNamespace(tokenizer=tok, language_model=lm)
+    ref.evaluate_model.clip.tokenize = lambda texts, truncate=True: clip_tokenize_ids(texts, ctx, sot, eot)
+    fx = {"Vc": Vc, "ctx": ctx, "w": w, "heads": heads, "out": out, "sot": sot, "eot": eot, "sd_text": pack_sd(export_clip_text(m)),
+          "runs": []}
+    for kw in (dict(max_decode_length=8, look_ahead=2, branching_factor=3, repetition_penalty=1.2),
+               dict(max_decode_length=6, look_ahead=1, branching_factor=2, repetition_penalty=1.0)):
+        outs = [ref.evaluate_model.generate_clip_guided("cpu", base["feat"][i:i + 1], model, ClipModel(), base["prefix"][i:i + 1], **kw)
+                for i in range(base["prefix"].shape[0])]
+        fx["runs"].append({"kw": kw, "captions": outs})
+    return fx
+
+
 def export_clip_text(hf):
     """HF CLIPTextModelWithProjection -> OpenAI CLIP text-tower names (token_embedding, positional_embedding,
     transformer.resblocks.N.*, ln_final, text_projection)."""
@@ -425,6 +480,12 @@ def make_loss_fixture():
 def main():
     ref = ref_harness.load_reference()
     os.makedirs(OUT, exist_ok=True)
+    if "--clip-guided" in sys.argv:
+        fx = make_clip_guided_fixture(ref, 27)
+        path = os.path.join(OUT, "tiny_clip_guided.pt")
+        torch.save(fx, path)
+        print(path, os.path.getsize(path) // 1024, "KiB", [r["captions"] for r in fx["runs"]])
+        return
     if "--acts" in sys.argv:
         fx = make_mapper_acts_fixture(ref, 26)
         path = os.path.join(OUT, "tiny_mapper_acts.pt")
