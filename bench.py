@@ -1,6 +1,6 @@
 """Benchmark of the caption-generation hot path on BASELINE.json's metric.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config 2|3|4|5]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
 Workload (BASELINE.json configs[1], the configuration the metric is quoted on): ViT-B/32 + 8-layer Transformer
@@ -17,6 +17,10 @@ replicated weights (weak scaling); the only collective is the final all-gather o
             library on its launching stream inside the timed region) against the measured HBM peak
   cpu_baseline / --impl reference: the reference's own algorithm (batch-1 loop, full re-forward every token, fp32;
             inference.py:70-148 with beam_size=1) restated by oracle/clipcap_oracle.py, on the host cores.
+
+--config selects another BASELINE.json configuration (the default, 2, is the one the metric is quoted on and the only one
+the CPU arm covers): 3 = nucleus sampling (top_p 0.9, temperature 1.0), batch 256; 4 = beam 5, 64 images per step (320
+rows, micro-batched by Engine.caption_dataset); 5 = GPT-J-6B + 4096-wide mapper, top_p 0.9, 16 images per GPU (128 on 8).
 """
 import argparse
 import json
@@ -38,6 +42,19 @@ UNIT = "captions/s"
 BATCH = 64
 NEW_TOKENS = 32
 WORKLOAD = "ViT-B/32 + 8-layer Transformer mapper (P=40, clip_len=40) + GPT2-XL, greedy, batch 64, 32 new tokens"
+# BASELINE.json configs[1..4] (1-based ids 2..5); `batch` is per GPU
+CONFIGS = {
+    2: dict(metric=METRIC, workload=WORKLOAD, batch=64, mode="greedy", beam=1, kw={}, lm={}),
+    3: dict(metric=METRIC, workload="config 2's model, nucleus sampling (top_p 0.9, temperature 1.0), batch 256, 32 new tokens",
+            batch=256, mode="sample", beam=1, kw=dict(top_p=0.9, temperature=1.0, seed=1), lm={}),
+    4: dict(metric=METRIC, workload="config 2's model, beam search (beam 5), 64 images per step (320 rows), 32 new tokens",
+            batch=64, mode="beam", beam=5, kw=dict(beam_size=5), lm={}),
+    5: dict(metric="captions/sec (GPT-J-6B, prefix 40, 32 tok)",
+            workload="ViT-B/32 + 8-layer Transformer mapper (d=4096) + GPT-J-6B, nucleus sampling (top_p 0.9), batch 16 per GPU "
+                     "(128 on 8 GPUs), 32 new tokens",
+            batch=16, mode="sample", beam=1, kw=dict(top_p=0.9, temperature=1.0, seed=1),
+            lm=dict(lm_arch="gptj", lm_d=4096, lm_layers=28, lm_heads=16, lm_vocab=50400, lm_n_pos=2048, lm_rotary_dim=64)),
+}
 
 
 def measured_hbm_peak():
@@ -66,6 +83,8 @@ def decode_step_bytes(cfg, batch, prefix_len, step):
     every bf16 weight once + K/V of the cached context read + K/V of the new token written."""
     d, L, V = cfg.lm_d, cfg.lm_layers, cfg.lm_vocab
     weights = 2 * (L * (12 * d * d + 13 * d) + 2 * d + V * d)
+    if cfg.lm_arch == "gptj":      # one LayerNorm per block, q/k/v/out without bias, untied biased head
+        weights = 2 * (L * (12 * d * d + 7 * d) + 2 * d + V * d + V * d + V)
     kv_tok = 2 * L * d * 2
     ctx = prefix_len + step - 1
     return weights + batch * ctx * kv_tok + batch * kv_tok
@@ -205,7 +224,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
     args = ap.parse_args()
+    C_ = CONFIGS[args.config]
+    BATCH = C_["batch"]
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     # stdout carries the JSON line and nothing else: whatever libraries print meanwhile (the "NCCL version ..." banner
     # of a box with NCCL_DEBUG set, ...) is sent to stderr
@@ -229,25 +251,32 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
-    cfg = cc.EngineConfig(max_images=BATCH, max_beam=1, max_ctx=40 + NEW_TOKENS + 8)
+    cfg = cc.EngineConfig(max_images=BATCH, max_beam=C_["beam"], max_ctx=40 + NEW_TOKENS + 8, **C_["lm"])
     eng = cc.Engine(cfg, local)
     synthetic.load_synthetic(eng, 1234)          # same seed on every rank: replicated weights
     torch.cuda.empty_cache()
     # every rank captions its own contiguous range of image ids
     images = synthetic.synthetic_images(BATCH, cfg, seed=rank, device=dev)
     host_images = images.cpu().pin_memory()
-    params = eng.gen_params("greedy", NEW_TOKENS, stop_token=-1, max_stops=0)
-    gathered = [torch.empty(BATCH, NEW_TOKENS, dtype=torch.int32, device=dev) for _ in range(world)] if world > 1 else None
+    params = eng.gen_params(C_["mode"], NEW_TOKENS, stop_token=-1, max_stops=0, **C_["kw"])
+    tok_shape = (BATCH, C_["beam"], NEW_TOKENS) if C_["mode"] == "beam" else (BATCH, NEW_TOKENS)
+    gathered = [torch.empty(tok_shape, dtype=torch.int32, device=dev) for _ in range(world)] if world > 1 else None
+
+    def caption(imgs):
+        if args.config == 2:
+            return eng.caption_images(imgs, params)
+        # micro-batches where one call does not cover the step (beam 5 x 64 images), Philox streams keyed by global image id
+        return eng.caption_dataset(imgs, params, first_row_id=rank * BATCH)
 
     def step_resident():
-        tokens, lengths, _ = eng.caption_images(images, params)
+        tokens, lengths, _ = caption(images)
         if world > 1:
             dist.all_gather(gathered, tokens)      # the only collective: final captions
         return tokens, lengths
 
     def step_e2e():
         dev_images = host_images.to(dev, non_blocking=True)
-        tokens, lengths, _ = eng.caption_images(dev_images, params)
+        tokens, lengths, _ = caption(dev_images)
         if world > 1:
             dist.all_gather(gathered, tokens)
         return tokens.cpu(), lengths.cpu()
@@ -287,8 +316,10 @@ def main():
     if profiled:
         torch.cuda.profiler.stop()
     launches = eng.launch_count - l0
-    n_sum = min(args.steps, 64)
+    calls_per_step = -(-BATCH // eng.micro_batch_for(params)) if args.config != 2 else 1
+    n_sum = min(args.steps * calls_per_step, 64)
     prefill_ms, decode_ms, decode_steps = eng.timing_sum(n_sum)
+    n_sum = n_sum / calls_per_step        # timed steps the sums cover
     for _ in range(2):
         step_e2e()
     e2e_ms_total, _ = timed(step_e2e, args.steps)
@@ -298,19 +329,20 @@ def main():
     value = world * BATCH / (ms_per_step * 1e-3)
     e2e_value = world * BATCH / (e2e_ms_total / args.steps * 1e-3)
     peak, peak_src = measured_hbm_peak()
-    step_bytes = sum(decode_step_bytes(cfg, BATCH, cfg.map_prefix_len, t) for t in range(1, NEW_TOKENS)) / (NEW_TOKENS - 1)
+    rows_per_launch = min(BATCH, eng.micro_batch_for(params)) * C_["beam"] if args.config != 2 else BATCH
+    step_bytes = sum(decode_step_bytes(cfg, rows_per_launch, cfg.map_prefix_len, t) for t in range(1, NEW_TOKENS)) / (NEW_TOKENS - 1)
     step_ms = decode_ms / max(decode_steps, 1)
     achieved = step_bytes / (step_ms * 1e-3) / 1e9
 
     if rank == 0:
         cpu = None
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and args.config == 2:
             cpu = cpu_baseline_leg()
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": C_["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "global_batch": BATCH * world,
+            "config": {"workload": C_["workload"], "baseline_config": args.config, "batch_per_gpu": BATCH, "global_batch": BATCH * world,
                        "new_tokens": NEW_TOKENS, "parallelism": "dp%d (replicated weights, sharded images)" % world,
                        "l2": "not flushed: every decode step streams 3.1 GB of weights + KV >> 126 MB L2",
                        "prefill_ms_per_step": prefill_ms / n_sum, "decode_ms_per_step": decode_ms / n_sum},
@@ -319,9 +351,10 @@ def main():
                     "d2h_bytes_per_step": tokens.numel() * 4 + lengths.numel() * 4},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": measured_traffic(),
-                         "kernel": "decode step = 1 CUDA-graph replay for 64 rows: decode_mega_kernel (all 48 layers, ~97% of "
-                                   "the step; `traffic` is its ncu DRAM bytes at step 2, context 41) + lm_head GEMM + argmax",
+                         "traffic": measured_traffic() if args.config == 2 else None,
+                         "kernel": ("decode step = 1 CUDA-graph replay for 64 rows: decode_mega_kernel (all 48 layers, ~97% of "
+                                    "the step; `traffic` is its ncu DRAM bytes at step 2, context 41) + lm_head GEMM + argmax")
+                         if args.config == 2 else "decode step = 1 CUDA-graph replay for %d rows (layer stack + lm_head + token selection)" % rows_per_launch,
                          "bytes_per_launch": step_bytes, "ms_per_launch": step_ms, "peak_source": peak_src},
             "cpu_baseline": cpu,
         }
