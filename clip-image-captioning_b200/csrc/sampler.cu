@@ -476,8 +476,11 @@ __global__ void __launch_bounds__(kSampThreads) top_p_kernel(const TopPArgs a) {
     }
   }
   // ---- typical filtering (sampling.py:72-102), on the row as filtered so far (sampling.py:205-206)
+  // (per-row budgets: every row is filtered, a budget of 0 keeps the most typical token, as in the reference when some
+  //  budget is positive; a NEGATIVE budget is this library's "leave the row alone" -- the device-side loop of
+  //  clipcap_b200.sampling.generate uses it when no active row has a positive budget)
   const float typ_p = a.typ_p_rows ? a.typ_p_rows[b] : a.typ_p;
-  if (a.typ_p_rows != nullptr || typ_p > 0.f) {
+  if ((a.typ_p_rows != nullptr && typ_p >= 0.f) || (a.typ_p_rows == nullptr && typ_p > 0.f)) {
     float s2 = 0.f;
     for (int v = threadIdx.x; v < V; v += blockDim.x) s2 += expf(vals[v] - mx);
     s2 = block_sum(s2, fscratch);

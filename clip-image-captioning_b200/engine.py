@@ -303,7 +303,9 @@ class Engine:
                    beam_size: int = 1, seed: int = 0, q_noise: Optional[torch.Tensor] = None,
                    row_ids: Optional[torch.Tensor] = None, top_p_rows: Optional[torch.Tensor] = None,
                    top_k_rows: Optional[torch.Tensor] = None, typ_p: float = 0.0,
-                   typ_p_rows: Optional[torch.Tensor] = None):
+                   typ_p_rows: Optional[torch.Tensor] = None, normalized: bool = False):
+        """`normalized=True`: the per-row budgets already follow the kernel's conventions (top_p_rows <= 0 / typ_p_rows < 0 =
+        leave the row alone) -- no host-side inspection of device tensors, hence no synchronisation."""
         p = GenParams()
         p.mode = {"greedy": _lib.GEN_GREEDY, "sample": _lib.GEN_SAMPLE, "beam": _lib.GEN_BEAM}[mode]
         p.max_new_tokens, p.stop_token, p.max_stops, p.eos_token = max_new_tokens, stop_token, max_stops, eos_token
@@ -324,7 +326,9 @@ class Engine:
             # sampling.py:149-160: with a tensor of budgets the nucleus filter runs on EVERY row as soon as one budget is
             # positive, and a row whose budget is <= 0 then keeps its top-1 token only (cumsum > top_p holds everywhere);
             # the kernel skips rows with a budget <= 0, so those get the smallest positive budget instead
-            if bool((top_p_rows > 0).any()):
+            if normalized:
+                pass
+            elif bool((top_p_rows > 0).any()):
                 top_p_rows = torch.where(top_p_rows > 0, top_p_rows, torch.full_like(top_p_rows, 1e-30))
             else:
                 top_p_rows = None

@@ -107,107 +107,108 @@ def clip_rank(engine: Engine, image: torch.Tensor, text_tokens: torch.Tensor):
     return cos_sim(text_features, image_features).reshape(-1).tolist()
 
 
-def _filter_kwargs(V: int, top_k, top_p, typ_p):
-    """Per-step sampler parameters from the reference's mixed scalar / tensor arguments (sampling.py:114-162, 72-102)."""
-    kw = {}
-    if torch.is_tensor(top_k):
-        if bool(torch.any(top_k > 0)):
-            k = top_k.clone().float()
-            frac = (k > 0) & (k < 1)
-            k[frac] = torch.clamp((k[frac] * V).floor(), min=1)
-            kw["top_k_rows"] = k.clamp(min=0, max=V).to(torch.int32)
-            kw["top_k"] = 1
-    else:
-        if isinstance(top_k, float):
-            top_k = max(1, int(top_k * V)) if 0 < top_k < 1 else int(top_k)
-        kw["top_k"] = min(int(top_k), V)
-    if torch.is_tensor(top_p):
-        if bool(torch.any(top_p > 0)):
-            kw["top_p_rows"] = top_p.reshape(-1).float()
-            kw["top_p"] = 1.0
-    else:
-        kw["top_p"] = float(top_p)
-    if torch.is_tensor(typ_p):
-        if bool(torch.any(typ_p > 0)):
-            kw["typ_p_rows"] = typ_p.reshape(-1).float()
-    elif typ_p > 0.0:
-        kw["typ_p"] = float(typ_p)
-    return kw
-
-
 @torch.no_grad()
 def generate(model, inputs: Optional[torch.Tensor], encoder_hidden_states, encoder_attention_mask, eos_token_id, top_p, top_k,
              typ_p, min_length, max_length, repetition_penalty: Optional[float] = None, min_alternate_prob=0,
              force_eos_log_prob=math.log(0.9), engine: Engine = None,
-             noise_fn: Optional[Callable[[int, int], torch.Tensor]] = None):
+             noise_fn: Optional[Callable[[int, int], torch.Tensor]] = None, check_every: int = 8):
     """sampling.py:165-268: the batched sampling loop with per-row min / max length, top-p / top-k / typical budgets, EOS
     masking before the minimum length, forced completion on a high EOS probability, and the alternate-sample fallback
-    (`torch.multinomial(p, 2)`).  `model.forward(input_ids=..., encoder_hidden_states=..., ...)` is called exactly as in the
-    reference (any decoder with that surface); everything per step after the logits -- EOS mask, repetition penalty,
-    filters, the two draws without replacement -- is ONE launch of the fused sampler kernel.  `noise_fn(rows, V)` supplies
-    the Exp(1) noise of the multinomial contract (default: the device RNG); returns the reference's list of
-    [tokens, min_length, max_length, top_p, eos_log_probs] groups in completion order."""
+    (`torch.multinomial(p, 2)`).  `model.forward(input_ids=..., encoder_hidden_states=..., ...)` is called as in the
+    reference (any decoder with that surface).
+
+    The loop state lives on the device and no step reads it back: rows are never compacted (a finished row keeps its slot
+    and is masked), completion, the alternate continuation and the per-row budgets of the rows still active are elementwise
+    device operations, everything between the logits and the two draws without replacement is ONE launch of the fused
+    sampler kernel, and the reference's result groups (rows in completion order, a row that continues on its alternate
+    sample is reported at that step too, sampling.py:230-246) are assembled after the last step from a [step, row] record.
+    Every `check_every` steps one flag is read to stop early once every row has finished.
+    `noise_fn(rows, V)` replays the reference's RNG stream (Exp(1) noise of the multinomial contract for the rows still
+    active, in row order); it needs the active count on the host, i.e. one read per step -- a test aid.  Default: the
+    device RNG for all rows.  Returns the reference's list of [tokens, min_length, max_length, top_p, eos_log_probs]."""
     eng = _engine_of(inputs, engine)
     dev = eng.device
-    total_max_length = int(max_length.max())
-    results = []
+    total = int(max_length.max())
     inputs = inputs.to(dev)
+    B, L0 = inputs.shape
+    tokens = torch.zeros(B, L0 + total, dtype=inputs.dtype, device=dev)
+    tokens[:, :L0] = inputs
     min_length, max_length = min_length.to(dev), max_length.to(dev)
-    top_p = top_p.to(dev) if torch.is_tensor(top_p) else top_p
-    top_k = top_k.to(dev) if torch.is_tensor(top_k) else top_k
-    typ_p = typ_p.to(dev) if torch.is_tensor(typ_p) else typ_p
-    eos_probs = torch.empty(inputs.size(0), 0, device=dev)
+    tp_rows = top_p.to(dev).reshape(-1).float() if torch.is_tensor(top_p) else None
+    ty_rows = typ_p.to(dev).reshape(-1).float() if torch.is_tensor(typ_p) else None
+    tk_rows = top_k.to(dev).reshape(-1).float() if torch.is_tensor(top_k) else None
+    active = torch.ones(B, dtype=torch.bool, device=dev)
+    reported = torch.zeros(total, B, dtype=torch.bool, device=dev)
+    eos_probs = torch.zeros(B, total, device=dev)
     cfg = getattr(model, "config", None)
-    for i in range(total_max_length):
-        if inputs.size(0) == 0:
+    use_pen = repetition_penalty is not None and repetition_penalty > 0
+    want_alt = min_alternate_prob > 0
+    steps = 0
+    for i in range(total):
+        if check_every and i and i % check_every == 0 and not bool(active.any()):
             break
-        outputs = model.forward(input_ids=inputs, encoder_hidden_states=encoder_hidden_states,
+        outputs = model.forward(input_ids=tokens[:, :L0 + i], encoder_hidden_states=encoder_hidden_states,
                                 encoder_attention_mask=encoder_attention_mask, return_dict=True,
                                 output_attentions=getattr(cfg, "output_attentions", False),
                                 output_hidden_states=getattr(cfg, "output_hidden_states", False))
         last = outputs["logits"][:, -1, :].to(dev, torch.float32).clone()
-        B, V = last.shape
+        V = last.shape[1]
         eos_prob = torch.log_softmax(last, dim=-1)[:, eos_token_id]          # raw_p[:, eos].log()
-        last[i < min_length, eos_token_id] = float("-inf")
-        q = noise_fn(B, V).to(dev, torch.float32) if noise_fn is not None else torch.empty(B, V, device=dev).exponential_(1)
-        kw = _filter_kwargs(V, top_k, top_p, typ_p)
-        use_pen = repetition_penalty is not None and repetition_penalty > 0
-        p = eng.gen_params("sample", 1, q_noise=q, repetition_penalty=float(repetition_penalty) if use_pen else 1.0, **kw)
-        nxt, filtered, alt = eng.sample(last, p, history=inputs if use_pen else None, return_filtered=True, return_alt=True)
-        next_token = nxt.long().unsqueeze(-1)
-        completed = torch.logical_or(next_token.squeeze(-1) == eos_token_id, max_length <= i)
+        last[:, eos_token_id].masked_fill_(i < min_length, float("-inf"))
+        if noise_fn is not None:
+            q = torch.ones(B, V, device=dev)
+            q[active] = noise_fn(int(active.sum()), V).to(dev, torch.float32)
+        else:
+            q = torch.empty(B, V, device=dev).exponential_(1)
+        kw = {}
+        if tk_rows is not None:          # per row: k <= 0 leaves the row alone, a fraction means that share of V (sampling.py:140-148)
+            k = torch.where((tk_rows > 0) & (tk_rows < 1), torch.clamp((tk_rows * V).floor(), min=1), tk_rows)
+            kw["top_k_rows"], kw["top_k"] = k.clamp(min=0, max=V).to(torch.int32), 1
+        else:
+            kw["top_k"] = min(max(1, int(top_k * V)) if isinstance(top_k, float) and 0 < top_k < 1 else int(top_k), V)
+        if tp_rows is not None:          # sampling.py:149: the filter runs on every row as soon as one ACTIVE budget is positive
+            some = ((tp_rows > 0) & active).any()
+            kw["top_p_rows"] = torch.where(tp_rows > 0, tp_rows, torch.where(some, 1e-30, 0.0).expand(B))
+            kw["top_p"] = 1.0
+        else:
+            kw["top_p"] = float(top_p)
+        if ty_rows is not None:          # sampling.py:77: likewise; a negative budget tells the kernel to skip the row
+            some = ((ty_rows > 0) & active).any()
+            kw["typ_p_rows"] = torch.where(some, ty_rows.clamp(min=0.0), torch.full_like(ty_rows, -1.0))
+        elif typ_p > 0.0:
+            kw["typ_p"] = float(typ_p)
+        p = eng.gen_params("sample", 1, q_noise=q, repetition_penalty=float(repetition_penalty) if use_pen else 1.0,
+                           normalized=True, **kw)
+        nxt, filtered, alt = eng.sample(last, p, history=tokens[:, :L0 + i] if use_pen else None, return_filtered=want_alt,
+                                        return_alt=want_alt)
+        nxt = nxt.long()
+        completed = (nxt == eos_token_id) | (max_length <= i)
         if force_eos_log_prob < 0:
-            completed = torch.logical_or(completed, eos_prob > force_eos_log_prob)
-        if bool(torch.any(completed)):
-            results.append([inputs[completed], min_length[completed], max_length[completed],
-                            top_p[completed] if torch.is_tensor(top_p) else top_p, eos_probs[completed]])
-            if min_alternate_prob > 0:
-                potential_continue = torch.logical_and(completed, max_length > i)
-                if bool(torch.any(potential_continue)):
-                    alternate_sample = alt.long().unsqueeze(-1)
-                    probs = torch.softmax(filtered, dim=-1)
-                    alternate_probs = torch.gather(probs, -1, alternate_sample)
-                    potential_continue = torch.logical_and(potential_continue, alternate_sample.squeeze(-1) != eos_token_id)
-                    potential_continue = torch.logical_and(potential_continue, alternate_probs.squeeze(-1) > min_alternate_prob)
-                    if bool(torch.any(potential_continue)):
-                        next_token[potential_continue] = alternate_sample[potential_continue]
-                        completed = torch.logical_and(completed, torch.logical_not(potential_continue))
-            keep = torch.logical_not(completed)
-            inputs, eos_prob, eos_probs, next_token = inputs[keep], eos_prob[keep], eos_probs[keep], next_token[keep]
-            if torch.is_tensor(top_p):
-                top_p = top_p[keep]
-            if torch.is_tensor(top_k):
-                top_k = top_k[keep]
-            if torch.is_tensor(typ_p):
-                typ_p = typ_p[keep]
-            min_length, max_length = min_length[keep], max_length[keep]
-            keep_h = keep.to(encoder_hidden_states.device)
-            encoder_hidden_states = encoder_hidden_states[keep_h]
-            encoder_attention_mask = encoder_attention_mask[keep_h]
-        inputs = torch.cat([inputs, next_token], dim=-1)
-        eos_probs = torch.cat([eos_probs, eos_prob.unsqueeze(-1)], dim=-1)
-    if inputs.size(0) > 0:
-        results.append([inputs, min_length, max_length, top_p, eos_probs])
+            completed |= eos_prob > force_eos_log_prob
+        completed &= active
+        reported[i] = completed
+        if want_alt:
+            alt = alt.long()
+            alt_p = torch.softmax(filtered, dim=-1).gather(-1, alt.unsqueeze(-1)).squeeze(-1)
+            go_on = completed & (max_length > i) & (alt != eos_token_id) & (alt_p > min_alternate_prob)
+            nxt = torch.where(go_on, alt, nxt)
+            completed = completed & ~go_on
+        active = active & ~completed
+        tokens[:, L0 + i] = nxt
+        eos_probs[:, i] = eos_prob
+        steps = i + 1
+    # ---- the reference's groups (one read of the record)
+    results = []
+    rep = reported[:steps].cpu()
+    tp_out = top_p.to(dev) if torch.is_tensor(top_p) else top_p
+    for i in range(steps):
+        if bool(rep[i].any()):
+            rows = rep[i].to(dev)
+            results.append([tokens[rows, :L0 + i], min_length[rows], max_length[rows],
+                            tp_out[rows] if torch.is_tensor(tp_out) else tp_out, eos_probs[rows, :i]])
+    if bool(active.any()):
+        results.append([tokens[active, :L0 + steps], min_length[active], max_length[active],
+                        tp_out[active] if torch.is_tensor(tp_out) else tp_out, eos_probs[active, :steps]])
     return results
 
 
