@@ -344,7 +344,8 @@ def main():
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": C_["workload"], "baseline_config": args.config, "batch_per_gpu": BATCH, "global_batch": BATCH * world,
                        "new_tokens": NEW_TOKENS, "parallelism": "dp%d (replicated weights, sharded images)" % world,
-                       "l2": "not flushed: every decode step streams 3.1 GB of weights + KV >> 126 MB L2",
+                       "l2": "not flushed: every decode step streams %.1f GB of weights + KV >> 126 MB L2"
+                             % (decode_step_bytes(cfg, 0, 0, 1) / 1e9),
                        "prefill_ms_per_step": prefill_ms / n_sum, "decode_ms_per_step": decode_ms / n_sum},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": host_images.numel() * host_images.element_size(),

@@ -61,7 +61,7 @@ __device__ __noinline__ void ln_phase(const MegaParams& p, ComputeCtx& cc, int c
     float s = 0.f;
     float4* hrow = reinterpret_cast<float4*>(hbase + static_cast<size_t>(t) * d);
     if (embed) {
-      const int tok = p.debug ? 0 : p.tokens[t];  // (debug modes compute garbage: keep the gather in range)
+      const int tok = p.tokens[t];
       const uint2* te = reinterpret_cast<const uint2*>(p.wte + static_cast<size_t>(tok) * d);
       const uint2* pe = p.wpe ? reinterpret_cast<const uint2*>(p.wpe + static_cast<size_t>(p.ctx_len[t]) * d) : nullptr;
 #pragma unroll 1
@@ -239,7 +239,6 @@ struct EpiCtx {
 // TMEM accumulator -> fp32 split-K partial in the workspace, for every segment of this CTA in GEMM `kind`.
 // Compute warp w reads TMEM lane quadrant w % 4 (its hardware-accessible quarter) and column half w / 4.
 __device__ __noinline__ void epilogue_phase(const MegaParams& p, ComputeCtx& cc, EpiCtx& ec, int cta, int kind, int layer) {
-  if ((p.debug & 1) != 0) return;
   // every field used below is copied to a register first: the partial stores could alias anything reached through
   // the references, and a reload per store costs more than the store
   const int rows_out = p.g[kind].rows_out, tbl_off = p.g[kind].tbl_off;
@@ -387,7 +386,6 @@ __global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const __grid_c
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
-  const bool skip_gemm = (p.debug & 1) != 0;
   const bool helper_prefetch = static_cast<uint32_t>(nX) * xstage <= 8u * 8192u;   // (see helper_attention)
 
   if (warp == 0) {
@@ -396,33 +394,31 @@ __global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const __grid_c
     //  the single-thread instructions without a per-instruction election loop)
     // Ring slots are handed over in PAIRS (two consecutive units of this CTA's stream share one full / empty barrier):
     // half the waits, expect_tx and commits per byte in all three role loops, which are what paces a GEMM phase.
-    if (!skip_gemm) {
-      uint32_t sp = 0, ph = 0;   // slot pair, its phase
-      const uint32_t nWp = static_cast<uint32_t>(nW / grp);
+    uint32_t sp = 0, ph = 0;   // slot pair, its phase
+    const uint32_t nWp = static_cast<uint32_t>(nW / grp);
 #pragma unroll 1
-      for (int l = 0; l < p.L; ++l) {
+    for (int l = 0; l < p.L; ++l) {
 #pragma unroll 1
-        for (int kind = 0; kind < 4; ++kind) {
-          const CUtensorMap* wm = p.wmaps + (l * 4 + kind);
-          const KindSched sc = sched[kind];
-          int tile = sc.tile0, kb = sc.kb0;
+      for (int kind = 0; kind < 4; ++kind) {
+        const CUtensorMap* wm = p.wmaps + (l * 4 + kind);
+        const KindSched sc = sched[kind];
+        int tile = sc.tile0, kb = sc.kb0;
 #pragma unroll 1
-          for (int n = sc.n; n > 0; n -= grp) {
-            const bool two = grp == 2 && n > 1;
-            ptx::mbar_wait(w_empty0 + 8u * sp, ph ^ 1);
-            if (ptx::elect_one()) {
-              const uint32_t full = w_full0 + 8u * sp;
-              ptx::mbar_arrive_expect_tx(full, two ? 2 * kWStage : kWStage);
-              ptx::tma_load_2d(w_ring + (grp * sp) * kWStage, wm, full, kb * 64, tile * 128, ptx::kEvictFirst);
-              int kb2 = kb + 1, tile2 = tile;
-              if (kb2 == sc.kb) { kb2 = 0; ++tile2; }
-              if (two) ptx::tma_load_2d(w_ring + (grp * sp + 1) * kWStage, wm, full, kb2 * 64, tile2 * 128, ptx::kEvictFirst);
-            }
-            __syncwarp();
-            if (++sp == nWp) { sp = 0; ph ^= 1; }
-            kb += grp;
-            while (kb >= sc.kb) { kb -= sc.kb; ++tile; }
+        for (int n = sc.n; n > 0; n -= grp) {
+          const bool two = grp == 2 && n > 1;
+          ptx::mbar_wait(w_empty0 + 8u * sp, ph ^ 1);
+          if (ptx::elect_one()) {
+            const uint32_t full = w_full0 + 8u * sp;
+            ptx::mbar_arrive_expect_tx(full, two ? 2 * kWStage : kWStage);
+            ptx::tma_load_2d(w_ring + (grp * sp) * kWStage, wm, full, kb * 64, tile * 128, ptx::kEvictFirst);
+            int kb2 = kb + 1, tile2 = tile;
+            if (kb2 == sc.kb) { kb2 = 0; ++tile2; }
+            if (two) ptx::tma_load_2d(w_ring + (grp * sp + 1) * kWStage, wm, full, kb2 * 64, tile2 * 128, ptx::kEvictFirst);
           }
+          __syncwarp();
+          if (++sp == nWp) { sp = 0; ph ^= 1; }
+          kb += grp;
+          while (kb >= sc.kb) { kb -= sc.kb; ++tile; }
         }
       }
     }
@@ -430,135 +426,127 @@ __global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const __grid_c
     // ------------------------------------------------------------------ X producer (+ attention helper)
     ComputeCtx hc;
     init_attn_ctx(p, hc, 8, kAttnWarps, lane, cta, tbl, gen + nW * kWStage, x_ring, strips);
-    if (skip_gemm) {
-      for (int l = 0; l < p.L; ++l) helper_attention<true>(p, hc, cta, l, vgo, vdone, helper_prefetch);
-    } else {
-      uint32_t s = 0, ph = 0;
+    uint32_t s = 0, ph = 0;
 #pragma unroll 1
-      for (int l = 0; l < p.L; ++l) {
+    for (int l = 0; l < p.L; ++l) {
 #pragma unroll 1
-        for (int kind = 0; kind < 4; ++kind) {
-          if (kind == 1) helper_attention<true>(p, hc, cta, l, vgo, vdone, helper_prefetch);   // between the c_attn and the c_proj tiles
-          const CUtensorMap* xm = (kind == 1) ? &xmap_att : (kind == 3) ? &xmap_mlp : &xmap_x;
-          const KindSched sc = sched[kind];
-          if (sc.n == 0) continue;
-          // the activation is complete once every CTA passed barrier #(8l + 2 kind) (the vector phase before it);
-          // no point in polling before this CTA's own compute warps arrived there (their (4l + kind)-th signal)
-          ptx::mbar_wait(xgo, static_cast<uint32_t>(4 * l + kind) & 1u);
+      for (int kind = 0; kind < 4; ++kind) {
+        if (kind == 1) helper_attention<true>(p, hc, cta, l, vgo, vdone, helper_prefetch);   // between the c_attn and the c_proj tiles
+        const CUtensorMap* xm = (kind == 1) ? &xmap_att : (kind == 3) ? &xmap_mlp : &xmap_x;
+        const KindSched sc = sched[kind];
+        if (sc.n == 0) continue;
+        // the activation is complete once every CTA passed barrier #(8l + 2 kind) (the vector phase before it);
+        // no point in polling before this CTA's own compute warps arrived there (their (4l + kind)-th signal)
+        ptx::mbar_wait(xgo, static_cast<uint32_t>(4 * l + kind) & 1u);
+        if (lane == 0) {
+          poll_counter(p.sync, static_cast<unsigned>(8 * l + 2 * kind + 1) * ncta);
+          fence_proxy_async_all();
+          MEGA_RSTAMP(l, kind * 8 + 0);
+        }
+        __syncwarp();
+        int kb = sc.kb0;
+#pragma unroll 1
+        for (int n = sc.n; n > 0; n -= grp) {
+          const bool two = grp == 2 && n > 1;
+          ptx::mbar_wait(x_empty0 + 8u * s, ph ^ 1);
           if (lane == 0) {
-            poll_counter(p.sync, static_cast<unsigned>(8 * l + 2 * kind + 1) * ncta);
-            fence_proxy_async_all();
-            MEGA_RSTAMP(l, kind * 8 + 0);
+            const uint32_t full = x_full0 + 8u * s;
+            ptx::mbar_arrive_expect_tx(full, two ? 2 * xstage : xstage);
+            ptx::tma_load_2d(x_ring + (grp * s) * xstage, xm, full, kb * 64, 0, ptx::kEvictLast);
+            int kb2 = kb + 1;
+            if (kb2 == sc.kb) kb2 = 0;
+            if (two) ptx::tma_load_2d(x_ring + (grp * s + 1) * xstage, xm, full, kb2 * 64, 0, ptx::kEvictLast);
           }
           __syncwarp();
-          int kb = sc.kb0;
-#pragma unroll 1
-          for (int n = sc.n; n > 0; n -= grp) {
-            const bool two = grp == 2 && n > 1;
-            ptx::mbar_wait(x_empty0 + 8u * s, ph ^ 1);
-            if (lane == 0) {
-              const uint32_t full = x_full0 + 8u * s;
-              ptx::mbar_arrive_expect_tx(full, two ? 2 * xstage : xstage);
-              ptx::tma_load_2d(x_ring + (grp * s) * xstage, xm, full, kb * 64, 0, ptx::kEvictLast);
-              int kb2 = kb + 1;
-              if (kb2 == sc.kb) kb2 = 0;
-              if (two) ptx::tma_load_2d(x_ring + (grp * s + 1) * xstage, xm, full, kb2 * 64, 0, ptx::kEvictLast);
-            }
-            __syncwarp();
-            if (++s == static_cast<uint32_t>(nX / grp)) { s = 0; ph ^= 1; }
-            kb += grp;
-            while (kb >= sc.kb) kb -= sc.kb;
-          }
-          if (lane == 0) MEGA_RSTAMP(l, kind * 8 + 1);
+          if (++s == static_cast<uint32_t>(nX / grp)) { s = 0; ph ^= 1; }
+          kb += grp;
+          while (kb >= sc.kb) kb -= sc.kb;
         }
+        if (lane == 0) MEGA_RSTAMP(l, kind * 8 + 1);
       }
     }
   } else if (warp == 2) {
     // ------------------------------------------------------------------ MMA issuer (+ attention helper)
     ComputeCtx hc;
     init_attn_ctx(p, hc, 9, kAttnWarps, lane, cta, tbl, gen + nW * kWStage, x_ring, strips);
-    if (skip_gemm) {
-      for (int l = 0; l < p.L; ++l) helper_attention<true>(p, hc, cta, l, vgo, vdone, helper_prefetch);
-    } else {
-      // The issue loop is instruction bound (one warp, dependent address arithmetic in front of every tcgen05.mma), so
-      // it works on slot PAIRS: one set of waits, one descriptor computation (kept incrementally, no multiplies) and
-      // one pair of ring commits per two units; the segment bookkeeping of both units is done ahead of the waits.
-      const uint32_t idesc = ptx::umma_idesc_bf16(128, p.N);
-      const uint64_t wdesc0 = ptx::umma_desc_k_sw128(w_ring), xdesc0 = ptx::umma_desc_k_sw128(x_ring);
-      const uint64_t wstep = static_cast<uint64_t>(kWStage >> 4), xstep = static_cast<uint64_t>(xstage >> 4);
-      uint64_t wd = wdesc0, xd = xdesc0;                    // descriptors of the current slot pair
-      uint32_t ws = 0, wph = 0, xs = 0, xph = 0, ait = 0;   // slot PAIRS and their phases
-      const uint32_t nWp = static_cast<uint32_t>(nW / grp), nXp = static_cast<uint32_t>(nX / grp);
-      const uint32_t nacc = static_cast<uint32_t>(p.N);
+    // The issue loop is instruction bound (one warp, dependent address arithmetic in front of every tcgen05.mma), so
+    // it works on slot PAIRS: one set of waits, one descriptor computation (kept incrementally, no multiplies) and
+    // one pair of ring commits per two units; the segment bookkeeping of both units is done ahead of the waits.
+    const uint32_t idesc = ptx::umma_idesc_bf16(128, p.N);
+    const uint64_t wdesc0 = ptx::umma_desc_k_sw128(w_ring), xdesc0 = ptx::umma_desc_k_sw128(x_ring);
+    const uint64_t wstep = static_cast<uint64_t>(kWStage >> 4), xstep = static_cast<uint64_t>(xstage >> 4);
+    uint64_t wd = wdesc0, xd = xdesc0;                    // descriptors of the current slot pair
+    uint32_t ws = 0, wph = 0, xs = 0, xph = 0, ait = 0;   // slot PAIRS and their phases
+    const uint32_t nWp = static_cast<uint32_t>(nW / grp), nXp = static_cast<uint32_t>(nX / grp);
+    const uint32_t nacc = static_cast<uint32_t>(p.N);
 #pragma unroll 1
-      for (int l = 0; l < p.L; ++l) {
+    for (int l = 0; l < p.L; ++l) {
 #pragma unroll 1
-        for (int kind = 0; kind < 4; ++kind) {
-          if (kind == 1) helper_attention<true>(p, hc, cta, l, vgo, vdone, helper_prefetch);   // all c_attn MMAs of this CTA are issued
-          const KindSched sc = sched[kind];
-          int kb = sc.kb0;          // k block of the next unit inside its row tile
-          int seg_left = 0;         // units left in the current segment (0: the next unit opens one)
-          uint32_t buf = 0;
+      for (int kind = 0; kind < 4; ++kind) {
+        if (kind == 1) helper_attention<true>(p, hc, cta, l, vgo, vdone, helper_prefetch);   // all c_attn MMAs of this CTA are issued
+        const KindSched sc = sched[kind];
+        int kb = sc.kb0;          // k block of the next unit inside its row tile
+        int seg_left = 0;         // units left in the current segment (0: the next unit opens one)
+        uint32_t buf = 0;
 #pragma unroll 1
-          for (int n = sc.n; n > 0; n -= grp) {
-            const bool two = grp == 2 && n > 1;
-            // ---- segment bookkeeping of both units (a segment = the rest of a row tile or of this CTA's range)
-            bool first0 = false, first1 = false;
+        for (int n = sc.n; n > 0; n -= grp) {
+          const bool two = grp == 2 && n > 1;
+          // ---- segment bookkeeping of both units (a segment = the rest of a row tile or of this CTA's range)
+          bool first0 = false, first1 = false;
+          if (seg_left == 0) {
+            seg_left = sc.kb - kb;
+            if (seg_left > n) seg_left = n;
+            buf = ait & 1;
+            ptx::mbar_wait(t_empty0 + 8u * buf, ((ait >> 1) & 1) ^ 1);
+            ++ait;
+            first0 = true;
+          }
+          const uint32_t buf0 = buf;
+          const bool end0 = --seg_left == 0;
+          if (++kb == sc.kb) kb = 0;
+          bool end1 = false;
+          if (two) {
             if (seg_left == 0) {
               seg_left = sc.kb - kb;
-              if (seg_left > n) seg_left = n;
+              if (seg_left > n - 1) seg_left = n - 1;
               buf = ait & 1;
               ptx::mbar_wait(t_empty0 + 8u * buf, ((ait >> 1) & 1) ^ 1);
               ++ait;
-              first0 = true;
+              first1 = true;
             }
-            const uint32_t buf0 = buf;
-            const bool end0 = --seg_left == 0;
+            end1 = --seg_left == 0;
             if (++kb == sc.kb) kb = 0;
-            bool end1 = false;
-            if (two) {
-              if (seg_left == 0) {
-                seg_left = sc.kb - kb;
-                if (seg_left > n - 1) seg_left = n - 1;
-                buf = ait & 1;
-                ptx::mbar_wait(t_empty0 + 8u * buf, ((ait >> 1) & 1) ^ 1);
-                ++ait;
-                first1 = true;
-              }
-              end1 = --seg_left == 0;
-              if (++kb == sc.kb) kb = 0;
-            }
-            const uint32_t buf1 = buf;
-            ptx::mbar_wait(w_full0 + 8u * ws, wph);
-            ptx::mbar_wait(x_full0 + 8u * xs, xph);
-            ptx::tc_fence_after();
-            if (ptx::elect_one()) {
-              if (first0) MEGA_RSTAMP(l, kind * 8 + 2);
-              const uint32_t tacc0 = tmem_base + buf0 * nacc;
-              ptx::umma_bf16(tacc0, wd, xd, idesc, first0 ? 0u : 1u);
-              ptx::umma_bf16(tacc0, wd + 2u, xd + 2u, idesc, 1u);
-              ptx::umma_bf16(tacc0, wd + 4u, xd + 4u, idesc, 1u);
-              ptx::umma_bf16(tacc0, wd + 6u, xd + 6u, idesc, 1u);
-              if (end0) ptx::umma_commit(t_full0 + 8u * buf0);
-              if (two) {
-                const uint32_t tacc1 = tmem_base + buf1 * nacc;
-                const uint64_t wd1 = wd + wstep, xd1 = xd + xstep;
-                ptx::umma_bf16(tacc1, wd1, xd1, idesc, first1 ? 0u : 1u);
-                ptx::umma_bf16(tacc1, wd1 + 2u, xd1 + 2u, idesc, 1u);
-                ptx::umma_bf16(tacc1, wd1 + 4u, xd1 + 4u, idesc, 1u);
-                ptx::umma_bf16(tacc1, wd1 + 6u, xd1 + 6u, idesc, 1u);
-                if (end1) ptx::umma_commit(t_full0 + 8u * buf1);
-              }
-              ptx::umma_commit(w_empty0 + 8u * ws);
-              ptx::umma_commit(x_empty0 + 8u * xs);
-              if (n <= grp) MEGA_RSTAMP(l, kind * 8 + 3);
-            }
-            __syncwarp();
-            wd += grp * wstep;
-            xd += grp * xstep;
-            if (++ws == nWp) { ws = 0; wph ^= 1; wd = wdesc0; }
-            if (++xs == nXp) { xs = 0; xph ^= 1; xd = xdesc0; }
           }
+          const uint32_t buf1 = buf;
+          ptx::mbar_wait(w_full0 + 8u * ws, wph);
+          ptx::mbar_wait(x_full0 + 8u * xs, xph);
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            if (first0) MEGA_RSTAMP(l, kind * 8 + 2);
+            const uint32_t tacc0 = tmem_base + buf0 * nacc;
+            ptx::umma_bf16(tacc0, wd, xd, idesc, first0 ? 0u : 1u);
+            ptx::umma_bf16(tacc0, wd + 2u, xd + 2u, idesc, 1u);
+            ptx::umma_bf16(tacc0, wd + 4u, xd + 4u, idesc, 1u);
+            ptx::umma_bf16(tacc0, wd + 6u, xd + 6u, idesc, 1u);
+            if (end0) ptx::umma_commit(t_full0 + 8u * buf0);
+            if (two) {
+              const uint32_t tacc1 = tmem_base + buf1 * nacc;
+              const uint64_t wd1 = wd + wstep, xd1 = xd + xstep;
+              ptx::umma_bf16(tacc1, wd1, xd1, idesc, first1 ? 0u : 1u);
+              ptx::umma_bf16(tacc1, wd1 + 2u, xd1 + 2u, idesc, 1u);
+              ptx::umma_bf16(tacc1, wd1 + 4u, xd1 + 4u, idesc, 1u);
+              ptx::umma_bf16(tacc1, wd1 + 6u, xd1 + 6u, idesc, 1u);
+              if (end1) ptx::umma_commit(t_full0 + 8u * buf1);
+            }
+            ptx::umma_commit(w_empty0 + 8u * ws);
+            ptx::umma_commit(x_empty0 + 8u * xs);
+            if (n <= grp) MEGA_RSTAMP(l, kind * 8 + 3);
+          }
+          __syncwarp();
+          wd += grp * wstep;
+          xd += grp * xstep;
+          if (++ws == nWp) { ws = 0; wph ^= 1; wd = wdesc0; }
+          if (++xs == nXp) { xs = 0; xph ^= 1; xd = xdesc0; }
         }
       }
     }
@@ -606,7 +594,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_mega_kernel(const __grid_c
       if (sched[0].n == 0) grid_wait(cc, 8 * l + 1);  // (see grid_arrive: no arrival at #k+1 before #k is complete)
       grid_arrive(cc, 0, 0, 0, false);       // #8l+1 (split-K partials: read with ld.global.cg, no TMA consumer)
       // (warp 0 polls the barrier for the CTA: it goes straight to the wait and fetches its K/V afterwards)
-      if ((p.debug & 4) == 0 && cc.cw != 0) attention_phase<true>(p, cc, cta, l, ly.b_qkv, true);
+      if (cc.cw != 0) attention_phase<true>(p, cc, cta, l, ly.b_qkv, true);
       grid_wait(cc, 8 * l + 2);
       if (cc.ct == 0) ptx::mbar_arrive(vgo);   // the helper warps start their units
       attention_phase<true>(p, cc, cta, l, ly.b_qkv, false);
@@ -707,8 +695,6 @@ int mega_launch(const MegaParams& p_in, cudaStream_t s) {
   if (p.grp == 2) p.nW &= ~1;
   if (p.nW < 2) return static_cast<int>(cudaErrorInvalidValue);
   {
-    const char* dbg = getenv("CCB_MEGA_DEBUG");
-    p.debug = dbg ? atoi(dbg) : 0;
     const char* lay = getenv("CCB_MEGA_LAYERS");  // tuning / debugging only: run the first n layers
     if (lay && atoi(lay) > 0 && atoi(lay) < p.L) p.L = atoi(lay);
   }

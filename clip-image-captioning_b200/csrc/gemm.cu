@@ -148,10 +148,6 @@ int launch_persist(const GemmArgs& a, const GemmParams& p_in, int bn, bool pair,
   pp.stages = stages;
   pp.m_tiles = pair ? (a.tokens + 255) / 256 : (a.tokens + 127) / 128;
   pp.n_tiles = (a.features + bn - 1) / bn;
-  {
-    const char* dbg = getenv("CCB_GEMM_DEBUG");
-    pp.debug = dbg ? atoi(dbg) : 0;
-  }
   CUtensorMap tx, tw;
   if (make_tmap(&tx, a.act, a.tokens, a.K, a.lda, 128)) return -1;
   if (make_tmap(&tw, a.weight, a.features, a.K, a.K, pair ? bn / 2 : bn)) return -1;

@@ -24,7 +24,6 @@ struct PersistParams {
   int bn;           // tile width in features (multiple of 32, <= 256)
   int stages;       // TMA ring depth
   int m_tiles, n_tiles;
-  int debug;        // tuning only (CCB_GEMM_DEBUG): 1 = no TMA loads (MMA on stale tiles), 2 = no MMAs (TMA only)
 };
 
 constexpr int kPersistThreads = 224;
@@ -45,13 +44,6 @@ __device__ __forceinline__ void persist_epilogue_tile(const PersistParams& pp, u
   long long out_row = i;
   if (p.rg_in > 0) out_row = static_cast<long long>(i / p.rg_in) * p.rg_out + p.rg_off + (i % p.rg_in);
   const bool vec_ok = ((p.ldo & 7) == 0) && (p.residual == nullptr || (p.ldr & 3) == 0);
-  if (pp.debug & 32) out_row = i & 127;   // tuning: all tiles store into the same 128 rows (no DRAM write-back)
-  if (pp.debug & 4) {   // tuning: no epilogue at all
-    ptx::tc_fence_before();
-    __syncwarp();
-    if (lane == 0) release();
-    return;
-  }
 #pragma unroll 1
   for (int c0 = 0; c0 < BN; c0 += 32) {
     const int j0 = row_b0 + c0;
@@ -64,7 +56,6 @@ __device__ __forceinline__ void persist_epilogue_tile(const PersistParams& pp, u
       __syncwarp();
       if (lane == 0) release();
     }
-    if (pp.debug & 8) continue;   // tuning: TMEM reads only
     float acc[32];
 #pragma unroll
     for (int v = 0; v < 32; ++v) acc[v] = __uint_as_float(r[v]);
@@ -125,18 +116,14 @@ __global__ void __launch_bounds__(kPersistThreads, 1) gemm_persist_kernel(const 
       const uint64_t hint = is_x ? ptx::kEvictLast : ptx::kEvictNormal;
       uint32_t s = 0, ph = 0;
 #pragma unroll 1
-      for (int tile = blockIdx.x; tile < ntiles && (pp.debug & 64) == 0; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int row = is_x ? (tile % pp.m_tiles) * 128 : (tile / pp.m_tiles) * BN;
 #pragma unroll 1
         for (int kb = 0; kb < nkb; ++kb) {
           ptx::mbar_wait(empty0 + 8u * s, ph ^ 1);
           if (ptx::elect_one()) {
-            if (pp.debug & 1) {   // tuning: no TMA loads
-              if (is_x) ptx::mbar_arrive(full0 + 8u * s);
-            } else {
-              if (is_x) ptx::mbar_arrive_expect_tx(full0 + 8u * s, stage_bytes);
-              ptx::tma_load_2d(smem_base + s * stage_bytes + off, tm, full0 + 8u * s, kb * 64, row, hint);
-            }
+            if (is_x) ptx::mbar_arrive_expect_tx(full0 + 8u * s, stage_bytes);
+            ptx::tma_load_2d(smem_base + s * stage_bytes + off, tm, full0 + 8u * s, kb * 64, row, hint);
           }
           __syncwarp();
           if (++s == static_cast<uint32_t>(S)) { s = 0; ph ^= 1; }
@@ -162,18 +149,16 @@ __global__ void __launch_bounds__(kPersistThreads, 1) gemm_persist_kernel(const 
         const uint32_t tacc = tmem_base + buf * 256u;
 #pragma unroll 1
         for (int kb = 0; kb < nkb; ++kb) {
-          if ((pp.debug & 64) == 0) ptx::mbar_wait(full0 + 8u * s, ph);   // (64: tuning, free-running issue loop)
+          ptx::mbar_wait(full0 + 8u * s, ph);
           ptx::tc_fence_after();
           if (ptx::elect_one()) {
             const uint64_t adesc = desc0 + static_cast<uint64_t>((s * stage_bytes) >> 4);
             const uint64_t bdesc = adesc + static_cast<uint64_t>((128u * 128u) >> 4);
-            if ((pp.debug & 2) == 0) {
-              ptx::umma_bf16(tacc, adesc, bdesc, idesc, kb > 0 ? 1u : 0u);
-              ptx::umma_bf16(tacc, adesc + 2u, bdesc + 2u, idesc, 1u);
-              ptx::umma_bf16(tacc, adesc + 4u, bdesc + 4u, idesc, 1u);
-              ptx::umma_bf16(tacc, adesc + 6u, bdesc + 6u, idesc, 1u);
-            }
-            if ((pp.debug & 64) == 0) ptx::umma_commit(empty0 + 8u * s);
+            ptx::umma_bf16(tacc, adesc, bdesc, idesc, kb > 0 ? 1u : 0u);
+            ptx::umma_bf16(tacc, adesc + 2u, bdesc + 2u, idesc, 1u);
+            ptx::umma_bf16(tacc, adesc + 4u, bdesc + 4u, idesc, 1u);
+            ptx::umma_bf16(tacc, adesc + 6u, bdesc + 6u, idesc, 1u);
+            ptx::umma_commit(empty0 + 8u * s);
             if (kb == nkb - 1) ptx::umma_commit(tfull0 + 8u * buf);
           }
           __syncwarp();
@@ -275,12 +260,8 @@ __global__ void __launch_bounds__(kPersistThreads, 1) gemm_pair_kernel(const __g
         for (int kb = 0; kb < nkb; ++kb) {
           ptx::mbar_wait(empty0 + 8u * s, ph ^ 1);
           if (ptx::elect_one()) {
-            if (pp.debug & 1) {   // tuning: no TMA loads
-              if (is_x && leader) ptx::mbar_arrive(full0 + 8u * s);
-            } else {
-              if (is_x && leader) ptx::mbar_arrive_expect_tx(full0 + 8u * s, 2u * stage_bytes);
-              ptx::tma_load_2d_pair(smem_base + s * stage_bytes + off, tm, lfull0 + 8u * s, kb * 64, row, hint);
-            }
+            if (is_x && leader) ptx::mbar_arrive_expect_tx(full0 + 8u * s, 2u * stage_bytes);
+            ptx::tma_load_2d_pair(smem_base + s * stage_bytes + off, tm, lfull0 + 8u * s, kb * 64, row, hint);
           }
           __syncwarp();
           if (++s == static_cast<uint32_t>(S)) { s = 0; ph ^= 1; }
@@ -306,12 +287,10 @@ __global__ void __launch_bounds__(kPersistThreads, 1) gemm_pair_kernel(const __g
           if (ptx::elect_one()) {
             const uint64_t adesc = desc0 + static_cast<uint64_t>((s * stage_bytes) >> 4);
             const uint64_t bdesc = adesc + static_cast<uint64_t>((128u * 128u) >> 4);
-            if ((pp.debug & 2) == 0) {
-              ptx::umma_bf16_pair(tacc, adesc, bdesc, idesc, kb > 0 ? 1u : 0u);
-              ptx::umma_bf16_pair(tacc, adesc + 2u, bdesc + 2u, idesc, 1u);
-              ptx::umma_bf16_pair(tacc, adesc + 4u, bdesc + 4u, idesc, 1u);
-              ptx::umma_bf16_pair(tacc, adesc + 6u, bdesc + 6u, idesc, 1u);
-            }
+            ptx::umma_bf16_pair(tacc, adesc, bdesc, idesc, kb > 0 ? 1u : 0u);
+            ptx::umma_bf16_pair(tacc, adesc + 2u, bdesc + 2u, idesc, 1u);
+            ptx::umma_bf16_pair(tacc, adesc + 4u, bdesc + 4u, idesc, 1u);
+            ptx::umma_bf16_pair(tacc, adesc + 6u, bdesc + 6u, idesc, 1u);
             ptx::umma_commit_pair(empty0 + 8u * s, 3);
             if (kb == nkb - 1) ptx::umma_commit_pair(tfull0 + 8u * buf, 3);
           }

@@ -49,7 +49,6 @@ struct MegaParams {
   int nW, nX, sc_cap;          // ring depths, per-warp score capacity (floats)
   int grp;                     // units per ring hand-over (2: slot pairs, 1: single slots)
   int log2_page_tokens;
-  int debug;                   // tuning only: bit 0 = skip the GEMM roles (vector phases timed alone; results are garbage)
   int xring_bytes;             // X ring size (>= 64 KB: it doubles as the scratch of the vector phases)
   int nbar;                    // grid barriers per launch minus the exit barrier (8 * L): sizes the trace rows
   unsigned long long* trace;   // optional [ncta][2 * (8 * L + 1)] globaltimer stamps of CTA phases

@@ -396,20 +396,24 @@ class Engine:
         does not depend on the micro-batch size or on how the images were sharded over GPUs."""
         n = images.shape[0]
         mb = micro_batch or self.micro_batch_for(p)
-        toks, lens, scs, held = [], [], [], []
+        toks, lens, scs = [], [], []
         keep_ids = p.row_ids
+        # ONE id buffer, rewritten in place per micro-batch (stream-ordered behind the previous call): the captured decode
+        # step is keyed by the pointers it reads, so a fresh tensor per micro-batch would re-capture the graph every time
+        ids = None
+        if p.mode == _lib.GEN_SAMPLE and not p.q_noise:
+            ids = torch.empty(mb, dtype=torch.int64, device=self.device)
+            p.row_ids = ids.data_ptr()
         for lo in range(0, n, mb):
             hi = min(n, lo + mb)
-            ids = None
-            if p.mode == _lib.GEN_SAMPLE and not p.q_noise:
-                ids = torch.arange(first_row_id + lo, first_row_id + hi, dtype=torch.int64, device=self.device)
-                p.row_ids = ids.data_ptr()
+            if ids is not None:
+                ids[:hi - lo].copy_(torch.arange(first_row_id + lo, first_row_id + hi, dtype=torch.int64, device=self.device))
             t, l, sc = self.caption_images(images[lo:hi], p, append_bos)
-            held.append(ids)     # read by the kernels of this call: keep alive until the results are assembled
             toks.append(t)
             lens.append(l)
             scs.append(sc)
         p.row_ids = keep_ids
+        self._keep.append(ids)       # read by the kernels of the last call
         tokens, lengths = torch.cat(toks, 0), torch.cat(lens, 0)
         scores = torch.cat(scs, 0) if scs and scs[0] is not None else None
         return tokens, lengths, scores
