@@ -68,9 +68,9 @@ def measured_hbm_peak():
 
 def measured_traffic():
     """DRAM bytes of the dominant kernel of the decode step (the persistent layer-stack kernel), from the committed ncu
-    --set full capture (profiles/r1_decode_mega_ncu.json: dram__bytes_read.sum + dram__bytes_write.sum of one launch)."""
+    --set full capture (profiles/r2_decode_mega_ncu.json: dram__bytes_read.sum + dram__bytes_write.sum of one launch)."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_decode_mega_ncu.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2_decode_mega_ncu.json")) as f:
             j = json.load(f)
         k = j["launches"][0] if "launches" in j else j
         return float(k["dram__bytes_read.sum"]) + float(k["dram__bytes_write.sum"])
