@@ -128,6 +128,30 @@ def test_beam_search_against_the_reference_loop_at_full_size(full):
     assert same_best >= N - 1
 
 
+def test_config5_mapper_4096_wide_at_full_size():
+    """The mapper of BASELINE config 5 (GPT-J-6B: embedding width 4096, 8 heads -> head_dim 512, S = 40 + 40) against the fp32
+    oracle: prefix embeddings within 2e-2 (the head_dim-512 attention takes the scalar prefill kernel)."""
+    import clipcap_b200 as cc
+    from clipcap_b200 import synthetic
+    cfg = cc.EngineConfig(lm_arch="gptj", lm_d=4096, lm_layers=1, lm_heads=16, lm_vocab=50400, lm_n_pos=2048, lm_rotary_dim=64,
+                          map_heads=8, max_images=8, max_beam=1, max_ctx=80)
+    eng = cc.Engine(cfg)
+    sds = synthetic.load_synthetic(eng)
+    images = synthetic.synthetic_images(8, cfg, device="cuda")
+    feat = eng.vit_encode(images)
+    prefix = eng.map_prefix(feat)
+    ref = orc.mapper_forward(sds["mapper"], feat.float(), cfg.map_clip_len, cfg.map_heads, "relu")
+    assert prefix.shape == ref.shape == (8, cfg.map_prefix_len, 4096)
+    assert rel(prefix, ref) <= TOL
+    # ... and the prefix drives the language model: first-token logits of the one-layer GPT-J against the oracle
+    lm = orc.OracleLM(sds["lm"], "gptj", cfg.lm_heads, cfg.lm_rotary_dim)
+    ours = eng.lm_forward(prefix, last_only=True)
+    with torch.no_grad():
+        want = lm.logits(ref)[:, -1]
+    assert rel(ours, want) <= TOL
+    eng.close()
+
+
 def test_clip_text_tower_at_full_size():
     """CLIP ViT-B/32 text tower (49408 x 512, 77 tokens, 12 layers, 8 heads) against the fp32 oracle on the GPU."""
     import clipcap_b200 as cc
