@@ -6,26 +6,30 @@
 //   B  att = attention(qkv, KV cache)           E  h  += mlp Wfc2^T + b
 //   C  h  += att Wproj^T + b
 //
+// STATUS: correct (tests/test_gpu_mega.py, GPT2-XL tokens) and measured SLOWER than decode_mega.cu (4.4 vs 2.4 ms per step
+// on B200; DESIGN.md section 3.1b has the per-phase timeline and the reasons), so it is opt-in: CCB_MEGA2=1 or
+// ccb_debug_set_mega(ctx, 3).  Kept as the measured starting point of the cluster design.
+//
 // What went away are the phases that only folded split-K partials out of an L2 workspace (ln_1, ln_2, gelu, and the q/k/v
-// fold in front of attention).  A step at 64 rows is a chain of grid-wide hand-overs (~2 us each) and phases that are a
-// few dependent L2 round trips long; the weight stream (3.1 GB per step) is nowhere near the bound, the number of
-// phases is.  The means:
-//   * Thread-block clusters of 4 CTAs.  A weight matrix is cut into 128-feature row tiles; a tile belongs to ONE
-//     cluster, whose CTAs split K four ways.  The four fp32 partials [128 features x 64 rows] are reduce-scattered over
-//     distributed shared memory (CTA j of the cluster finalises rows 16 j .. 16 j + 15: every CTA pushes the rows of the
-//     other three with st.shared::cluster and signals a remote mbarrier), summed in rank order (deterministic) and
-//     finished in registers: bias, then bf16 q/k/v, or gelu_new -> bf16, or the fp32 residual update of h.
-//   * LayerNorm moved into the consumer.  The finaliser of a residual update knows h for 128 features x 16 rows, so it
-//     publishes the tile's (mean, M2) per row [tiles][64 rows]; a consumer CTA Chan-combines the 13 pairs of a row,
-//     reads its K slice of h (fp32, L2), normalises and writes the bf16 operand tile straight into the 128B-swizzled
-//     shared-memory layout tcgen05.mma reads.  No x round trip, no LayerNorm phase.
+// fold in front of attention).  The means:
+//   * Thread-block clusters of 4 CTAs.  A weight matrix is cut into 64-feature row tiles (tcgen05.mma M = 64: feature
+//     16 q + i of a tile lives in TMEM lane 32 q + i); a tile belongs to ONE cluster, whose CTAs split K four ways.  The
+//     four fp32 partials [64 features x 64 rows] are reduce-scattered over distributed shared memory (CTA j of the cluster
+//     finalises rows 16 j .. 16 j + 15: every CTA pushes the rows of the other three with 128-bit st.shared::cluster and
+//     signals a remote mbarrier), summed in rank order (deterministic) and finished in registers: bias, then bf16 q/k/v,
+//     or gelu_new -> bf16, or the fp32 residual update of h.
+//   * LayerNorm moved into the consumer.  The finaliser of a residual update knows h for 64 features x 16 rows, so it
+//     publishes the tile's (mean, M2) per row [tiles][64 rows]; a consumer CTA Chan-combines the pairs of a row (25 for
+//     d = 1600), reads its K slice of h (fp32, L2), normalises and writes the bf16 operand tile straight into the
+//     128B-swizzled shared-memory layout tcgen05.mma reads.  No x round trip, no LayerNorm phase.
 //   * Everything else as in decode_mega.cu: a W-producer warp that streams this CTA's weight tiles of ALL layers in
 //     consumption order through a TMA ring (it runs ahead across phases), an X-producer warp (TMA loads of att / mlp
-//     tiles), one MMA-issuer warp (tcgen05.mma 128 x 64 x 16, accumulators in TMEM), 8 compute warps, bounded spins.
+//     tiles), one MMA-issuer warp (tcgen05.mma 64 x 64 x 16, accumulators in TMEM), 8 compute warps, bounded spins; ring
+//     slots are handed over in chunks (up to 4 weight tiles / 16 MMAs per barrier wait).
 //   Warps 1-3 and two attention-only warps take attention units too (13 warps x 132 CTAs >= 64 rows x 25 heads).
 //
 // Tile -> cluster: tile t of GEMM kind k belongs to cluster (t + off_k) % ncl (host-planned offsets balance the bytes
-// each CTA streams); a cluster owns at most two tiles of a kind and runs them together (one X tile feeds both).
+// each CTA streams); a cluster owns at most four tiles of a kind and runs them together (one X tile feeds all of them).
 #include <cuda.h>
 #include <stdio.h>
 #include <stdlib.h>
