@@ -361,6 +361,207 @@ int launch_prefill_mma(const bf16* qkv, bf16* out, int B, int S, int H, int hd, 
   return e == cudaSuccess ? 0 : (int)e;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// tcgen05 / TMEM prefill attention for head_dim 64 and S <= 64 (ViT-B/32: S = 50; GPT-2 prefill of a 40-token prefix).
+// One CTA of four warps per (head, batch).  Q, K and V^T are staged by the threads as 128B-swizzled K-major tiles (what
+// a TMA box {64, 64 rows} would write; V is transposed on the way so that P.V has its K dimension = keys contiguous);
+// S = Q.K^T is ONE M = 64 x N = 64 accumulator in TMEM (4 tcgen05.mma of K = 16); the M = 64 accumulator keeps row
+// 16 w + i in lane i of warp w's quadrant, so lanes 0-15 of every warp own one query row each and do the whole softmax
+// in registers (no shuffles); P, normalised and split into bf16 hi + lo terms like the mma.sync kernel (same accuracy),
+// goes back through shared memory as the A operand of O = P.V (8 tcgen05.mma into a second accumulator).
+// K / V are appended to the paged cache while they are staged (write_cache), the HF key mask and the causal mask are
+// applied to the scores.  Rotary models (GPT-J) keep the mma.sync kernel.
+__device__ __forceinline__ void sts_u16(uint32_t addr, uint16_t v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// Q / K / V^T tiles (P_hi / P_lo reuse Q / K once S is computed) + key mask + barrier / TMEM slot + alignment: 8 CTAs per SM
+constexpr int kUmmaAttnSmem = 3 * 8192 + 64 * 4 + 64 + 1024;
+
+__global__ void __launch_bounds__(128) attention_prefill_umma_kernel(
+    const bf16* __restrict__ qkv, bf16* __restrict__ out, int S, int H, float scale, int causal, KvCache cache, int layer,
+    const int* __restrict__ block_table, int pos0, int write_cache, const uint8_t* __restrict__ key_mask) {
+  constexpr int HD = 64;
+  extern __shared__ uint8_t umma_smem[];
+  const uint32_t raw = ptx::smem_u32(umma_smem);
+  const uint32_t sb = (raw + 1023u) & ~1023u;
+  uint8_t* gen = umma_smem + (sb - raw);
+  const uint32_t q_s = sb, k_s = sb + 8192, vt_s = sb + 16384, ph_s = q_s, pl_s = k_s;
+  float* mask_add = reinterpret_cast<float*>(gen + 24576);
+  const uint32_t bar = sb + 24576 + 256, slot = bar + 16;
+  volatile uint32_t* slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + 24576 + 256 + 16);
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int d = H * HD;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    ptx::mbar_init(bar, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 0) ptx::tmem_alloc<64>(slot);   // S and, after the softmax has read it, O share the 64 columns
+  ptx::grid_dep_wait();     // qkv comes from the c_attn GEMM this kernel is chained behind (PDL)
+  ptx::grid_dep_launch();
+  // ---- stage Q and K (row-major, swizzled), append K to the cache, key mask; then S = Q K^T is issued ...
+  const bf16* base = qkv + static_cast<size_t>(b) * S * 3 * d + h * HD;
+  const int* bt = block_table + static_cast<size_t>(b) * cache.max_pages_per_row;
+  for (int idx = tid; idx < 64 * 8; idx += 128) {
+    const int j = idx >> 3, c = idx & 7;
+    uint4 qq = make_uint4(0u, 0u, 0u, 0u), kk = qq;
+    if (j < S) {
+      const bf16* rowp = base + static_cast<size_t>(j) * 3 * d + c * 8;
+      qq = *reinterpret_cast<const uint4*>(rowp);
+      kk = *reinterpret_cast<const uint4*>(rowp + d);
+      if (write_cache) {
+        const int pos = pos0 + j;
+        *reinterpret_cast<uint4*>(cache.base + kv_index(cache, layer, 0, bt[pos / cache.page_tokens], h, pos % cache.page_tokens) + c * 8) = kk;
+      }
+    }
+    const uint32_t off = static_cast<uint32_t>(j) * 128u + (static_cast<uint32_t>(c ^ (j & 7)) << 4);
+    sts_v4(q_s + off, qq);
+    sts_v4(k_s + off, kk);
+  }
+  if (tid < 64) mask_add[tid] = (tid < S && (key_mask == nullptr || key_mask[static_cast<size_t>(b) * S + tid])) ? 0.f : -INFINITY;
+  ptx::fence_proxy_async();          // generic stores -> tcgen05.mma (async proxy) reads
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *slot_ptr;
+  const uint32_t idesc = ptx::umma_idesc_bf16(64, 64);
+  if (warp == 0 && ptx::elect_one()) {
+    const uint64_t ad = ptx::umma_desc_k_sw128(q_s), bd = ptx::umma_desc_k_sw128(k_s);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) ptx::umma_bf16(tmem, ad + 2u * k, bd + 2u * k, idesc, k > 0 ? 1u : 0u);
+    ptx::umma_commit(bar);
+  }
+  // ---- ... while V is transposed: element (dim n, key j) -> row n, 16-byte chunk (j / 8) ^ (n % 8), slot j % 8.  A lane's
+  // eight elements are visited in an order rotated by its chunk index c, so that the eight lanes that share a key write
+  // eight different rows AND chunks (no bank conflicts; the loads stay 128 contiguous bytes per key)
+  for (int idx = tid; idx < 64 * 8; idx += 128) {
+    const int j = idx >> 3, c = idx & 7;
+    uint4 vv = make_uint4(0u, 0u, 0u, 0u);
+    if (j < S) {
+      vv = *reinterpret_cast<const uint4*>(base + static_cast<size_t>(j) * 3 * d + 2 * d + c * 8);
+      if (write_cache) {
+        const int pos = pos0 + j;
+        *reinterpret_cast<uint4*>(cache.base + kv_index(cache, layer, 1, bt[pos / cache.page_tokens], h, pos % cache.page_tokens) + c * 8) = vv;
+      }
+    }
+    const uint64_t lo64 = static_cast<uint64_t>(vv.x) | (static_cast<uint64_t>(vv.y) << 32);
+    const uint64_t hi64 = static_cast<uint64_t>(vv.z) | (static_cast<uint64_t>(vv.w) << 32);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int ee = (e + c) & 7, n = c * 8 + ee;
+      const uint16_t val = static_cast<uint16_t>(((ee & 4) ? hi64 : lo64) >> (16 * (ee & 3)));
+      sts_u16(vt_s + static_cast<uint32_t>(n) * 128u + (static_cast<uint32_t>((j >> 3) ^ (n & 7)) << 4) + static_cast<uint32_t>(j & 7) * 2u, val);
+    }
+  }
+  ptx::mbar_wait(bar, 0);
+  ptx::tc_fence_after();
+  // ---- softmax: lanes 0-15 of each warp hold the 64 scores of row 16 warp + lane; lanes 16-31 take the upper 32 columns
+  // of the same row over by shuffle, so that all 32 lanes work (half a row each)
+  const int row = warp * 16 + (lane & 15);
+  {
+    uint32_t r0[32], r1[32];
+    ptx::tmem_ld32(tmem + (static_cast<uint32_t>(warp * 32) << 16), r0);
+    ptx::tmem_ld32(tmem + (static_cast<uint32_t>(warp * 32) << 16) + 32u, r1);
+    ptx::tmem_ld_wait();
+    const bool upper = lane >= 16;
+    const int col0 = upper ? 32 : 0;
+    float sc[32];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const uint32_t hi_half = __shfl_sync(0xffffffffu, r1[j], lane & 15);
+      const float raw_s = __uint_as_float(upper ? hi_half : r0[j]);
+      const int key = col0 + j;
+      const float v = (causal && key > row) ? -INFINITY : raw_s * scale + mask_add[key];
+      sc[j] = v;
+      mx = fmaxf(mx, v);
+    }
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float pr = (sc[j] == -INFINITY) ? 0.f : expf(sc[j] - mx);
+      sc[j] = pr;
+      sum += pr;
+    }
+    sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+    const float inv = sum > 0.f ? 1.f / sum : 0.f;
+    const uint32_t roff = static_cast<uint32_t>(row) * 128u;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float x0 = sc[c * 8 + 2 * e] * inv, x1 = sc[c * 8 + 2 * e + 1] * inv;
+        hi[e] = pack_bf16x2(x0, x1);
+        const float2 hf = unpack_bf16x2(hi[e]);
+        lo[e] = pack_bf16x2(x0 - hf.x, x1 - hf.y);
+      }
+      const uint32_t off = roff + (static_cast<uint32_t>(((upper ? 4 : 0) + c) ^ (row & 7)) << 4);
+      sts_v4(ph_s + off, make_uint4(hi[0], hi[1], hi[2], hi[3]));
+      sts_v4(pl_s + off, make_uint4(lo[0], lo[1], lo[2], lo[3]));
+    }
+  }
+  ptx::fence_proxy_async();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  // ---- O = P V (hi and lo terms into one accumulator)
+  if (warp == 0 && ptx::elect_one()) {
+    const uint64_t ah = ptx::umma_desc_k_sw128(ph_s), al = ptx::umma_desc_k_sw128(pl_s), bd = ptx::umma_desc_k_sw128(vt_s);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) ptx::umma_bf16(tmem, ah + 2u * k, bd + 2u * k, idesc, k > 0 ? 1u : 0u);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) ptx::umma_bf16(tmem, al + 2u * k, bd + 2u * k, idesc, 1u);
+    ptx::umma_commit(bar);
+  }
+  ptx::mbar_wait(bar, 1);
+  ptx::tc_fence_after();
+  {
+    uint32_t r0[32], r1[32];
+    ptx::tmem_ld32(tmem + (static_cast<uint32_t>(warp * 32) << 16), r0);
+    ptx::tmem_ld32(tmem + (static_cast<uint32_t>(warp * 32) << 16) + 32u, r1);
+    ptx::tmem_ld_wait();
+    if (lane < 16 && row < S) {
+      bf16* op = out + (static_cast<size_t>(b) * S + row) * d + h * HD;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint4 pk;
+        const uint32_t* src = c < 4 ? r0 + c * 8 : r1 + (c - 4) * 8;
+        pk.x = pack_bf16x2(__uint_as_float(src[0]), __uint_as_float(src[1]));
+        pk.y = pack_bf16x2(__uint_as_float(src[2]), __uint_as_float(src[3]));
+        pk.z = pack_bf16x2(__uint_as_float(src[4]), __uint_as_float(src[5]));
+        pk.w = pack_bf16x2(__uint_as_float(src[6]), __uint_as_float(src[7]));
+        *reinterpret_cast<uint4*>(op + c * 8) = pk;
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<64>(tmem);
+  }
+}
+
+int launch_prefill_umma(const bf16* qkv, bf16* out, int B, int S, int H, float scale, int causal, const KvCache& c, int layer,
+                        const int* block_table, int pos0, int write_cache, const uint8_t* key_mask, cudaStream_t s) {
+  static bool configured_dev[kMaxDevices] = {};
+  bool& configured = configured_dev[current_device_slot()];
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attention_prefill_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kUmmaAttnSmem);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  cudaError_t e = launch_kernel(attention_prefill_umma_kernel, dim3(H, B), dim3(128), kUmmaAttnSmem, s, true, qkv, out, S, H, scale, causal,
+                                c, layer, block_table, pos0, write_cache, key_mask);
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
 template <int NT>
 int dispatch_prefill_mma_ks(int ks, const bf16* qkv, bf16* out, int B, int S, int H, int hd, float scale, int causal,
                             const KvCache& c, int layer, const int* bt, int pos0, int wc, const uint8_t* km, int rd, cudaStream_t s) {
@@ -682,6 +883,15 @@ int attention_prefill(const bf16* qkv, bf16* out, int B, int S, int H, int hd, f
     const char* e = getenv("CCB_ATTN_MMA");
     return !(e && e[0] == '0');
   }();
+  static const bool use_umma = [] {
+    const char* e = getenv("CCB_ATTN_UMMA");
+    return !(e && e[0] == '0');
+  }();
+  if (use_mma && use_umma && hd == 64 && S <= 64 && rotary_dim == 0) {   // tcgen05 / TMEM path (ViT, GPT-2 prefill)
+    KvCache c;
+    if (cache) c = *cache;
+    return launch_prefill_umma(qkv, out, B, S, H, scale, causal, c, layer, block_table, pos0, cache != nullptr ? 1 : 0, key_mask, s);
+  }
   if (use_mma && S <= 128 && hd % 8 == 0 && hd <= 256 && rotary_dim % 2 == 0) {
     KvCache c;
     if (cache) c = *cache;
