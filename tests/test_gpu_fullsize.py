@@ -82,10 +82,17 @@ def test_captions_do_not_depend_on_the_batch_split(xl, mode, kw):
     same = (whole == split).flatten(1).all(dim=1)
     # GEMM tiles see different row counts (5 / 1 / 10 vs 16 rows: other MMA shapes and split-K orders), so fp32 sums
     # may differ in the last bits and flip a near-tie; identical rows must dominate
-    assert same.float().mean().item() >= 0.8, same
-    if whole_sc is not None:
+    if whole_sc is None:
+        assert same.float().mean().item() >= 0.8, same
+    else:
+        # beam search: five hypotheses per image, any near-tie among 5 x 50 257 candidates per step may resolve differently
+        # (measured 12-13 of 16 images identical with either prefill-attention kernel); what must hold is that a different
+        # outcome is a TIE: the winning hypotheses' length-normalised scores agree within the bf16 tolerance
         split_sc = torch.cat([s for _, s in parts], dim=0)
+        assert same.float().mean().item() >= 0.6, same
         assert (whole_sc[same] - split_sc[same]).abs().max().item() <= 1e-2
+        best_w, best_s = whole_sc.max(-1).values, split_sc.max(-1).values
+        assert ((best_w - best_s).abs() <= 2e-2 * best_w.abs()).all(), (best_w, best_s)
 
 
 def test_sampling_is_keyed_by_global_image_id(xl):
