@@ -65,11 +65,16 @@ struct GemmCfg {
   static constexpr int kThreads = 192;
 };
 
+// per-CTA timeline stamps: compiled in only with -DCCB_TUNING (python tools/build.py --tuning)
+#ifdef CCB_TUNING
 #define CCB_TRACE(slot)                                                                                   \
   do {                                                                                                    \
     if (p.trace != nullptr && lane == 0)                                                                  \
       p.trace[((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8ull + (slot)] = ptx::globaltimer_ns(); \
   } while (0)
+#else
+#define CCB_TRACE(slot) do { } while (0)
+#endif
 
 // Fused epilogue on CW accumulator columns [c0, c0 + CW) of this thread's row.  Kept small on purpose: it runs
 // once per tile, so its instructions are cold in the instruction cache (a fully unrolled epilogue with the

@@ -56,11 +56,16 @@ __device__ __forceinline__ void poll_counter(const unsigned* ctr, unsigned targe
 
 // fine-grained role stamps of layer 1 (tuning only): slot k of CTA c at trace[ncta * 2 * (nbar + 2) + c * 64 + k], nbar = the
 // kernel's grid barriers per step (p.nbar)
+// Compiled in only with -DCCB_TUNING (python tools/build.py --tuning): production builds carry no timeline code.
+#ifdef CCB_TUNING
 #define MEGA_RSTAMP(layer, slot)                                                                         \
   do {                                                                                                   \
     if (p.trace != nullptr && (layer) == 1)                                                              \
       p.trace[static_cast<size_t>(p.ncta) * (2 * (p.nbar + 2)) + static_cast<size_t>(blockIdx.x) * 64 + (slot)] = ptx::globaltimer_ns(); \
   } while (0)
+#else
+#define MEGA_RSTAMP(layer, slot) do { } while (0)
+#endif
 
 // This CTA's share of one GEMM kind (the same in every layer): n units starting at (tile0, kb0), row-tile major.
 struct KindSched {
@@ -99,8 +104,12 @@ __device__ __forceinline__ float compute_sum(ComputeCtx& cc, float v) {
 }
 
 __device__ __forceinline__ void stamp(ComputeCtx& cc) {
+#ifdef CCB_TUNING
   if (cc.trace != nullptr && cc.ct == 0) cc.trace[cc.trace_it] = ptx::globaltimer_ns();
   cc.trace_it++;
+#else
+  (void)cc;
+#endif
 }
 
 // all compute threads: publish this CTA's global writes of the phase and count the CTA in.  The CTA barrier orders
@@ -117,7 +126,9 @@ __device__ __forceinline__ void grid_arrive(ComputeCtx& cc, uint32_t xgo_bar, ui
   if (cc.ct == 0) {
     if (helpers_bar != 0) {
       ptx::mbar_wait(helpers_bar, helpers_parity);  // the helper warps' share of the phase is stored
+#ifdef CCB_TUNING
       if (cc.rtrace != nullptr && cc.cur_layer == 1) cc.rtrace[44] = ptx::globaltimer_ns();
+#endif
     }
     if (proxy) fence_proxy_async_all();  // the global writes are read through TMA (async proxy) by other CTAs
     red_release_add(cc.ctr, 1u);

@@ -195,7 +195,8 @@ CCB_API int ccb_op_linear(ccb_ctx* ctx, const void* x, int64_t lda, int tokens, 
  * trace[(n % launches) * stride_u64 + cta * 8 + k] (entry, setup, first tile landed, MMAs issued, accumulator ready,
  * cluster reduction reached, epilogue done, exit).  NULL (the default) disables it. */
 CCB_API int ccb_debug_gemm_trace(ccb_ctx* ctx, void* trace_u64, int64_t stride_u64, int launches);
-/* tuning aid for the persistent decode-step kernel: when non-NULL every CTA writes globaltimer stamps of its phase
+/* tuning aid for the persistent decode-step kernel (inert unless the library was built with -DCCB_TUNING,
+ * `python tools/build.py --tuning`): when non-NULL every CTA writes globaltimer stamps of its phase
  * boundaries (grid-barrier waits / arrivals, in program order) to trace[cta * 2 * (8 * lm_layers + 2) + k].
  * Returns the number of CTAs of that kernel (0 when the model shape is not covered by it). */
 CCB_API int ccb_debug_mega_trace(ccb_ctx* ctx, void* trace_u64);

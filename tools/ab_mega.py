@@ -1,4 +1,5 @@
-"""A/B of the decode step: persistent kernel vs operator-per-kernel chain (GPT2-XL, synthetic weights).
+"""(Needs a library built with `python tools/build.py --tuning`: the timeline stamps are compiled out otherwise.)
+A/B of the decode step: persistent kernel vs operator-per-kernel chain (GPT2-XL, synthetic weights).
    python tools/ab_mega.py [B] [T] [mode] [trace]"""
 import sys, os, ctypes as C
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -62,7 +62,11 @@ def compile_one(nvcc, src, verbose):
     return obj
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, tuning=False):
+    """tuning=True compiles the per-CTA timeline stamps in (-DCCB_TUNING: tools/trace_*.py, tools/ab_mega.py need them)."""
+    if tuning:
+        force = True
+        NVCC_FLAGS.append("-DCCB_TUNING")
     if not force and up_to_date():
         return OUT
     nvcc = find_nvcc()
@@ -84,5 +88,6 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--force", action="store_true")
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--tuning", action="store_true", help="compile the timeline stamps in (-DCCB_TUNING)")
     a = ap.parse_args()
-    print(build(a.force, a.verbose))
+    print(build(a.force, a.verbose, a.tuning))

@@ -1,4 +1,5 @@
-"""Timeline of the GEMMs inside one replayed decode step (GPT2-XL, B=64): per launch, first CTA entry / last exit."""
+"""(Needs a library built with `python tools/build.py --tuning`: the timeline stamps are compiled out otherwise.)
+Timeline of the GEMMs inside one replayed decode step (GPT2-XL, B=64): per launch, first CTA entry / last exit."""
 import sys, os, ctypes as C
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch

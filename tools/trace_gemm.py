@@ -1,4 +1,5 @@
-"""Per-CTA timeline of the decode-shaped GEMM (ccb_debug_gemm_trace)."""
+"""(Needs a library built with `python tools/build.py --tuning`: the timeline stamps are compiled out otherwise.)
+Per-CTA timeline of the decode-shaped GEMM (ccb_debug_gemm_trace)."""
 import sys, os, ctypes as C
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch

@@ -1,4 +1,5 @@
-"""Phase timeline of the five-phase persistent decode kernel (decode_mega2.cu): per phase, over the CTAs, the time from
+"""(Needs a library built with `python tools/build.py --tuning`: the timeline stamps are compiled out otherwise.)
+Phase timeline of the five-phase persistent decode kernel (decode_mega2.cu): per phase, over the CTAs, the time from
 the phase's grid-barrier wait to the arrival at the next barrier, and the hand-over between them.
    python tools/trace_mega2.py [B] [layer]"""
 import ctypes as C
