@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libclipcap_b200.so")
+# CCB_LIB: another build of the same library (tools/build_variant.py: A/B measurements of kernel variants)
+LIB_PATH = os.environ.get("CCB_LIB") or os.path.join(_HERE, "libclipcap_b200.so")
 
 DTYPE_F32, DTYPE_F16, DTYPE_BF16 = 0, 1, 2
 LM_GPT2, LM_GPTJ = 0, 1

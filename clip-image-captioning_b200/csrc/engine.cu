@@ -1388,6 +1388,11 @@ int ccb_op_linear(ccb_ctx* c, const void* x, int64_t lda, int tokens, const void
   g.force_orientation = orientation;
   g.force_bn = bn;
   g.force_split = split_k;
+  static const bool op_pdl = [] {   // tuning (tools/bench_stream.py): chain back-to-back operator launches like the engine does
+    const char* e = getenv("CCB_OP_PDL");
+    return e && e[0] == '1';
+  }();
+  g.allow_pdl = op_pdl ? 1 : 0;
   RUN(gemm_launch(g, c->gemm_ws, static_cast<cudaStream_t>(stream)));
   return 0;
 }

@@ -38,4 +38,4 @@ for it in range(iters):
         it, ms, B / ms * 1e3, pre, dec, steps, dec / max(steps, 1), eng.launch_count - l0))
 if profile_last:
     torch.cuda.profiler.stop()
-print(tokens[0].tolist()[:16])
+print(tokens[0].tolist()[:16], "checksum", int((tokens.to(torch.int64) * torch.arange(1, tokens.numel() + 1, device=tokens.device).view_as(tokens)).sum().item()))
