@@ -371,7 +371,129 @@ struct TopPArgs {
   float* filtered_out;
   int* alt_out;
   int* next;
+  int fast;   // 1: try nucleus_sample_fast first
 };
+
+
+// ---- sampling from the nucleus WITHOUT finding its boundary (the common case: top-p only, nothing but the token asked for)
+// multinomial(softmax(filtered)) == argmax over the kept set S of p_v / q_v, and dividing by the kept mass does not change
+// the arg-max.  So: rank all tokens by r'_v = exp(x_v - max) / q_v, take the best few, and test them for membership in S in
+// that order -- "v is kept iff the probability mass ranked strictly before it is <= top_p" (see the header comment) is ONE
+// masked sum over the row, not a selection.  The first candidate inside S is the sample; it is accepted only if it leads the
+// next-ranked candidate by more than the rounding the exact path's extra division (p / kept_mass) could introduce (1e-6
+// relative, two fp32 roundings are 1.2e-7), so the result is the exact path's token, ties included.  Everything else --
+// no candidate in S among the first six (probability (1 - top_p)^6), a near-tie, a thread holding more than four of the
+// top seven -- falls through to the radix select below.  5 light passes over the row instead of 8 heavy ones + 2.
+struct Top4 {
+  float v[4];
+  int i[4];
+};
+__device__ __forceinline__ void top4_insert(Top4& t, float v, int i) {
+  // (v, i) ranks before (tv, ti) iff v > tv or (v == tv and i < ti)
+  if (!(v > t.v[3] || (v == t.v[3] && i < t.i[3]))) return;
+  int pos = 3;
+#pragma unroll
+  for (int k = 2; k >= 0; --k)
+    if (v > t.v[k] || (v == t.v[k] && i < t.i[k])) pos = k;
+#pragma unroll
+  for (int k = 3; k > 0; --k)
+    if (k > pos) { t.v[k] = t.v[k - 1]; t.i[k] = t.i[k - 1]; }
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (k == pos) { t.v[k] = v; t.i[k] = i; }
+}
+
+// returns the sampled token or -1 (block-uniform) when the exact path has to decide
+__device__ int nucleus_sample_fast(const float* vals, int V, float mx, float inv_sum, float top_p, const float* qrow,
+                                   unsigned long long seed, unsigned long long rid, uint32_t step, ArgMax* ascratch,
+                                   double* dscratch, int* iscratch) {
+  constexpr int NC = 7;   // candidates: six testable + one more for the last one's margin
+  Top4 loc;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { loc.v[k] = -INFINITY; loc.i[k] = 0x7fffffff; }
+  int seen = 0;
+  if (qrow != nullptr) {
+    for (int v = threadIdx.x; v < V; v += blockDim.x) {
+      const float x = vals[v];
+      if (x == -INFINITY) continue;
+      ++seen;
+      top4_insert(loc, expf(x - mx) / qrow[v], v);
+    }
+  } else {
+    for (int g = threadIdx.x; 4 * g < V; g += blockDim.x) {
+      float x[4];
+      bool any = false;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        x[k] = (4 * g + k < V) ? vals[4 * g + k] : -INFINITY;
+        any |= x[k] != -INFINITY;
+      }
+      if (!any) continue;
+      const float4 q4 = philox_exp1_x4(seed, rid, step, static_cast<uint32_t>(g));
+      const float q[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (x[k] == -INFINITY) continue;
+        ++seen;
+        top4_insert(loc, expf(x[k] - mx) / q[k], 4 * g + k);
+      }
+    }
+  }
+  // the block's best NC, in rank order: NC arg-max rounds, the owner of a winner pops it
+  float cv[NC];
+  int ci[NC];
+  int popped = 0;
+#pragma unroll
+  for (int j = 0; j < NC; ++j) {
+    ArgMax mine;
+    mine.v = loc.v[0];
+    mine.i = loc.i[0];
+    const ArgMax win = block_argmax(mine, ascratch);
+    cv[j] = win.v;
+    ci[j] = win.i;
+    if (win.i == loc.i[0] && loc.i[0] != 0x7fffffff) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { loc.v[k] = loc.v[k + 1]; loc.i[k] = loc.i[k + 1]; }
+      loc.v[3] = -INFINITY;
+      loc.i[3] = 0x7fffffff;
+      ++popped;
+    }
+  }
+  // a thread that gave all four of its entries away may hold a better fifth than what the block saw
+  if (__syncthreads_or(popped == 4 && seen > 4)) return -1;
+#pragma unroll 1
+  for (int j = 0; j + 1 < NC; j += 2) {
+    const int ia = ci[j], ib = ci[j + 1];
+    if (ia == 0x7fffffff) return -1;                  // fewer candidates than that: nothing left to test
+    const bool has_b = ib != 0x7fffffff;
+    const float xa = vals[ia], xb = has_b ? vals[ib] : 0.f;
+    const uint32_t ka = order_key(xa), kb = has_b ? order_key(xb) : 0xffffffffu;
+    const uint32_t klo = ka < kb ? ka : kb;
+    double ma = 0.0, mb = 0.0;
+    int ta = 0, tb = 0;
+    for (int v = threadIdx.x; v < V; v += blockDim.x) {
+      const float x = vals[v];
+      const uint32_t key = order_key(x);
+      if (key < klo) continue;
+      const double pm = static_cast<double>(expf(x - mx) * inv_sum);
+      if (key > ka) ma += pm;
+      else if (key == ka && v < ia) ++ta;
+      if (key > kb) mb += pm;
+      else if (key == kb && v < ib) ++tb;
+    }
+    ma = block_sum_d(ma, dscratch);
+    mb = block_sum_d(mb, dscratch);
+    ta = block_sum_i(ta, iscratch);
+    tb = block_sum_i(tb, iscratch);
+    const double pa = static_cast<double>(expf(xa - mx) * inv_sum), pb = static_cast<double>(expf(xb - mx) * inv_sum);
+    const bool in_a = !(static_cast<float>(ma + ta * pa) > top_p);
+    const bool in_b = has_b && !(static_cast<float>(mb + tb * pb) > top_p);
+    // (exp(x - max) > 1e-20 keeps p = exp / kept_mass a normal number, so the relative rounding bound above holds)
+    if (in_a) return (expf(xa - mx) > 1e-20f && cv[j] > cv[j + 1] * 1.000001f) ? ia : -1;
+    if (in_b) return (j + 2 < NC && expf(xb - mx) > 1e-20f && cv[j + 1] > cv[j + 2] * 1.000001f) ? ib : -1;
+  }
+  return -1;
+}
 
 __global__ void __launch_bounds__(kSampThreads) top_p_kernel(const TopPArgs a) {
   extern __shared__ float vals[];  // V floats
@@ -423,6 +545,20 @@ __global__ void __launch_bounds__(kSampThreads) top_p_kernel(const TopPArgs a) {
 
   // ---- top-p
   const float top_p = a.top_p_rows ? a.top_p_rows[b] : a.top_p;
+  {
+    const float typ = a.typ_p_rows ? a.typ_p_rows[b] : a.typ_p;
+    const bool typ_on = (a.typ_p_rows != nullptr && typ >= 0.f) || (a.typ_p_rows == nullptr && typ > 0.f);
+    if (a.fast && top_p > 0.f && !typ_on && a.filtered_out == nullptr && a.alt_out == nullptr) {
+      const unsigned long long rid_f = a.row_ids ? static_cast<unsigned long long>(a.row_ids[b]) : static_cast<unsigned long long>(b);
+      const uint32_t step_f = a.step ? static_cast<uint32_t>(*a.step) : static_cast<uint32_t>(a.step_scalar);
+      const float* qrow_f = a.q_noise ? a.q_noise + static_cast<long long>(step_f) * a.q_step_stride + static_cast<long long>(b) * a.ldq : nullptr;
+      const int tok = nucleus_sample_fast(vals, V, mx, 1.0f / sum, top_p, qrow_f, a.seed, rid_f, step_f, ascratch, dscratch, iscratch);
+      if (tok >= 0) {
+        if (threadIdx.x == 0) a.next[b] = tok;
+        return;
+      }
+    }
+  }
   if (top_p > 0.f) {
     const SelectResult r = radix_select(vals, V, 1, 0, top_p, mx, 1.0f / sum, dscratch, iscratch);
     if (r.reached) {
@@ -856,6 +992,11 @@ int sample_top_p(const float* logits, long long ld, int B, int V, const SamplePa
   a.q_noise = sp.q_noise; a.ldq = sp.ldq; a.q_step_stride = sp.q_step_stride; a.seed = sp.seed; a.row_ids = sp.row_ids;
   a.step = sp.step; a.step_scalar = sp.step_scalar;
   a.filtered_out = sp.filtered_out; a.alt_out = sp.alt_out; a.next = next;
+  static const bool fast_on = [] {   // CCB_SAMPLER_FAST=0: always the radix select (A/B)
+    const char* e = getenv("CCB_SAMPLER_FAST");
+    return !(e && e[0] == '0');
+  }();
+  a.fast = fast_on ? 1 : 0;
   top_p_kernel<<<B, kSampThreads, smem, s>>>(a);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
