@@ -601,6 +601,9 @@ int beam_select(ccb_ctx* c, const ccb_gen_params* p, int N, int T, bool first, c
   st.tokens = c->gen_tokens;
   st.max_len = T;
   st.step = c->step;
+  st.cand_scratch = c->beam_cand;
+  st.cand_rows = c->max_rows;
+  if (c->capturing) c->capture_launches++; else c->launches++;   // (beam_step launches two kernels)
   RUN(beam_step(c->logits, c->ldv, N, beam, c->desc.lm_vocab, p->temperature, p->stop_token, st, c->next_tokens,
                 c->src_rows, c->block_table, c->max_pages_per_row, c->ctx_len, s));
   return 0;
@@ -1039,6 +1042,7 @@ int ccb_create(ccb_ctx** out, const ccb_model_desc* desc, int device) {
   c->step = a.arr<int>(1);
   c->next_tokens = a.arr<int>(c->max_rows);
   c->src_rows = a.arr<int>(c->max_rows);
+  c->beam_cand = a.take(static_cast<size_t>(c->max_rows) * kBeamCandPerRow * 8);
   c->gen_tokens = a.arr<int>(static_cast<size_t>(c->max_rows) * D.max_ctx);
   c->lengths = a.arr<int>(c->max_rows);
   c->stops = a.arr<int>(c->max_rows);
@@ -1361,6 +1365,10 @@ int ccb_beam_step(ccb_ctx* c, const float* logits, int64_t ld, int N, int beam, 
   st.tokens = tokens;
   st.max_len = max_len;
   st.step = c->step;
+  st.cand_scratch = c->beam_cand;
+  st.cand_rows = c->max_rows;
+  if (N * beam > c->max_rows) return fail(c, "ccb_beam_step: N * beam = %d exceeds the context's %d rows", N * beam, c->max_rows);
+  c->launches++;   // (two kernels)
   RUN(beam_step(logits, ld, N, beam, V, temperature, stop_token, st, next_tokens, src_rows, nullptr, 0, nullptr, s));
   return 0;
 }

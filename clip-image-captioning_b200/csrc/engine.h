@@ -118,6 +118,7 @@ struct ccb_ctx {
   int* step = nullptr;            // [1]
   int* next_tokens = nullptr;     // [max_rows]
   int* src_rows = nullptr;        // [max_rows]
+  void* beam_cand = nullptr;      // [max_rows, kBeamCandPerRow] (value, flat index): beam_rows_kernel -> beam_merge_kernel
   int* gen_tokens = nullptr;      // [max_rows, max_ctx]
   int* lengths = nullptr;         // [max_rows]
   int* stops = nullptr;           // [max_rows]

@@ -192,7 +192,10 @@ struct BeamState {
   int* tokens = nullptr;         // [N, beam, max_len]
   int max_len = 0;
   const int* step = nullptr;     // device step counter: 0 = first step (topk over the single prefill row)
+  void* cand_scratch = nullptr;  // [cand_rows, kBeamCandPerRow] (value, flat index) pairs: the rows' best candidates
+  int cand_rows = 0;
 };
+constexpr int kBeamCandPerRow = 8;   // == kMaxBeam of sampler.cu
 int beam_step(const float* logits, long long ld, int N, int beam, int V, float temperature, int stop_token,
               const BeamState& st, int* next_tokens /*[N*beam]*/, int* src_rows /*[N*beam] global row ids*/,
               int* block_table /*[N*beam, max_pages] permuted in place, or null*/, int max_pages,

@@ -715,8 +715,18 @@ __global__ void __launch_bounds__(kSampThreads) top_p_kernel(const TopPArgs a) {
 //          len = len[src]; score = avg * len; stopped = stopped[src] | (tok == stop)
 // Also permutes the per-row token history and block tables so the next decode step reads the right KV.
 constexpr int kMaxBeam = 8;
+static_assert(kMaxBeam == kBeamCandPerRow, "candidate scratch rows are sized by internal.h");
+
+struct Cand {
+  float v;
+  int idx;  // flat index r * V + tok
+};
+__device__ __forceinline__ bool cand_better(const Cand& a, const Cand& b) {  // a ranks before b
+  return a.v > b.v || (a.v == b.v && a.idx < b.idx);
+}
 
 struct BeamArgs {
+  Cand* cand;               // [N*beam, kMaxBeam] the rows' best candidates (beam_rows_kernel -> beam_merge_kernel)
   const float* logits;      // step 0: [N, ld] (one row per image); later: [N*beam, ld]
   long long ld;
   int beam, V;
@@ -735,54 +745,192 @@ struct BeamArgs {
   const int* ctx_len;       // [N*beam] tokens currently cached per row (entries < ctx are permuted)
 };
 
-struct Cand {
-  float v;
-  int idx;  // flat index r * V + tok
-};
-__device__ __forceinline__ bool cand_better(const Cand& a, const Cand& b) {  // a ranks before b
-  return a.v > b.v || (a.v == b.v && a.idx < b.idx);
-}
+// Two launches per step.  beam_rows_kernel: one CTA per (image, beam row) -- the row's log-softmax statistics and its
+// best kMaxBeam candidates (255 rows keep every SM busy where one CTA per image used 51 of 148).  beam_merge_kernel: one
+// CTA per image merges the rows' candidate lists (the top-beam of the union is the top-beam of the union of the rows'
+// top-beams) and does the bookkeeping.
+constexpr int kBeamRowThreads = 512;
 
-__global__ void __launch_bounds__(kSampThreads) beam_step_kernel(const BeamArgs a) {
+__global__ void __launch_bounds__(kBeamRowThreads, 2) beam_rows_kernel(const BeamArgs a) {
   __shared__ float fscratch[32];
-  __shared__ float row_max[kMaxBeam], row_lse_sum[kMaxBeam];
-  __shared__ Cand wcand[32 * kMaxBeam];
-  __shared__ Cand top[kMaxBeam];
-  __shared__ float s_scores[kMaxBeam], s_len[kMaxBeam];
-  __shared__ uint8_t s_stop[kMaxBeam];
-  extern __shared__ int perm_buf[];  // beam * max(max_len, max_pages) ints
-  const int n = blockIdx.x;
+  __shared__ Cand wcand[(kBeamRowThreads / 32) * kMaxBeam];
   const int beam = a.beam, V = a.V;
+  const int n = blockIdx.x / beam, r = blockIdx.x - n * beam;
   const int step = *a.step;
   const bool first = (step == 0);
-  const int rows = first ? 1 : beam;
+  if (first && r > 0) return;          // the first step ranks the single prefill row of the image
+  Cand* out = a.cand + static_cast<long long>(blockIdx.x) * kMaxBeam;
   const float T = a.temperature > 0.f ? a.temperature : 1.0f;
-
-  if (threadIdx.x < beam) {
-    s_scores[threadIdx.x] = first ? 0.f : a.scores[n * beam + threadIdx.x];
-    s_len[threadIdx.x] = first ? 1.f : a.seq_lengths[n * beam + threadIdx.x];
-    s_stop[threadIdx.x] = first ? 0 : a.has_stopped[n * beam + threadIdx.x];
-  }
-  __syncthreads();
+  const bool unit_T = T == 1.0f;       // x / 1.0f == x: skip the division
+  const float score = first ? 0.f : a.scores[n * beam + r];
+  const bool stopped = !first && a.has_stopped[n * beam + r];
   // seq_lengths[~has_stopped] += 1  (not on the first step)
-  if (!first && threadIdx.x < beam && !s_stop[threadIdx.x]) s_len[threadIdx.x] += 1.f;
-
-  // per-row softmax statistics
-  for (int r = 0; r < rows; ++r) {
-    const float* row = a.logits + (first ? static_cast<long long>(n) : static_cast<long long>(n) * beam + r) * a.ld;
-    float mx = -INFINITY;
-    for (int v = threadIdx.x; v < V; v += blockDim.x) mx = fmaxf(mx, row[v] / T);
-    mx = block_max(mx, fscratch);
-    float sm = 0.f;
-    for (int v = threadIdx.x; v < V; v += blockDim.x) sm += expf(row[v] / T - mx);
-    sm = block_sum(sm, fscratch);
-    if (threadIdx.x == 0) {
-      row_max[r] = mx;
-      row_lse_sum[r] = sm;
+  const float len = first ? 1.f : a.seq_lengths[n * beam + r] + (stopped ? 0.f : 1.f);
+  if (stopped) {
+    // logits[has_stopped] = -inf; logits[has_stopped, 0] = 0  -> only token 0 is a finite candidate
+    if (threadIdx.x < kMaxBeam) {
+      Cand c;
+      c.v = threadIdx.x == 0 ? (score + 0.f) / len : -INFINITY;
+      c.idx = threadIdx.x == 0 ? r * V : 0x7fffffff;
+      out[threadIdx.x] = c;
+    }
+    return;
+  }
+  const float* row = a.logits + (first ? static_cast<long long>(n) : static_cast<long long>(n) * beam + r) * a.ld;
+  // The row (L2-resident: the lm_head has just written it) is walked three times.  With one scalar load in flight per
+  // thread the walks are bound by the L2 latency (32 warps x 128 B per ~700 cycles); each thread therefore takes groups
+  // of four consecutive logits (one 16-byte load when the row is aligned) and requests four groups before it uses the
+  // first.  A thread still meets its tokens in ascending index order, which the tie rule below relies on.
+  const bool vec = (reinterpret_cast<uintptr_t>(row) & 15) == 0;
+  const int nq = (V + 3) >> 2;
+  auto load4 = [&](int q, float (&x)[4]) {
+    if (q >= nq) {
+      x[0] = x[1] = x[2] = x[3] = -INFINITY;
+    } else if (vec && 4 * q + 3 < V) {
+      const float4 t = *reinterpret_cast<const float4*>(row + 4 * q);
+      x[0] = t.x; x[1] = t.y; x[2] = t.z; x[3] = t.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) x[e] = (4 * q + e < V) ? row[4 * q + e] : -INFINITY;
+    }
+  };
+  const int qstep = blockDim.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  // ---- walk 1: every thread's largest logit.  The beam-th largest of these thread maxima is a lower bound t0 of the
+  // row's beam-th largest logit (they are `beam` different tokens), and hardly any token but those lies above it.
+  float tmax = -INFINITY;
+  for (int q0 = threadIdx.x; q0 < nq; q0 += 4 * qstep) {
+    float x[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) load4(q0 + u * qstep, x[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) tmax = fmaxf(tmax, x[u][e]);   // (-inf padding is neutral)
+  }
+  __shared__ float wtop[(kBeamRowThreads / 32) * kMaxBeam];
+  __shared__ float s_t0, s_xmax;
+  {
+    float v = tmax;
+    for (int k = 0; k < kMaxBeam; ++k) {   // the warp's k-th largest thread maximum
+      float m = v;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      if (lane == 0) wtop[w * kMaxBeam + k] = m;
+      const unsigned holders = __ballot_sync(0xffffffffu, v == m);
+      if (lane == __ffs(holders) - 1) v = -INFINITY;
     }
   }
   __syncthreads();
+  if (w == 0) {
+    float h[(kBeamRowThreads / 32) * kMaxBeam / 32];   // 4 values per lane
+#pragma unroll
+    for (int j = 0; j < (kBeamRowThreads / 32) * kMaxBeam / 32; ++j) {
+      const int i = lane + 32 * j;
+      h[j] = i < nw * kMaxBeam ? wtop[i] : -INFINITY;
+    }
+    float m = -INFINITY;
+    for (int k = 0; k < beam; ++k) {
+      float best = -INFINITY;
+      int bj = 0;
+#pragma unroll
+      for (int j = 0; j < (kBeamRowThreads / 32) * kMaxBeam / 32; ++j)
+        if (h[j] > best) { best = h[j]; bj = j; }
+      m = best;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      if (k == 0 && lane == 0) s_xmax = m;
+      const unsigned holders = __ballot_sync(0xffffffffu, best == m);
+      if (lane == __ffs(holders) - 1) {
+#pragma unroll
+        for (int j = 0; j < (kBeamRowThreads / 32) * kMaxBeam / 32; ++j)
+          if (j == bj) h[j] = -INFINITY;
+      }
+    }
+    if (lane == 0) s_t0 = m;
+  }
+  __shared__ int s_ncand;
+  if (threadIdx.x == 0) s_ncand = 0;
+  __syncthreads();
+  const float xmax = s_xmax, t0 = s_t0;
+  const float mx = unit_T ? xmax : xmax / T;     // == max of x / T: the division is monotone
+  // The candidate value below is a non-decreasing function of the logit up to the rounding of expf / logf (< 1e-5 in the
+  // log-probability, i.e. < 1e-5 T in the logit): every member of the row's top-beam has a logit above t0 minus that; the
+  // margin taken is a hundred times wider.
+  const float thr = t0 - (1e-3f * T + 1e-6f * fabsf(t0));
+  constexpr int kCap = 128;
+  __shared__ int cidx[kCap];
+  __shared__ Cand cval[kCap];
+  // ---- walk 2: softmax denominator; tokens above the threshold are noted
+  float sm = 0.f;
+  for (int q0 = threadIdx.x; q0 < nq; q0 += 4 * qstep) {
+    float x[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) load4(q0 + u * qstep, x[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        sm += expf((unit_T ? x[u][e] : x[u][e] / T) - mx);   // exp(-inf) == 0
+        if (x[u][e] >= thr && x[u][e] != -INFINITY) {
+          const int pos = atomicAdd(&s_ncand, 1);
+          if (pos < kCap) cidx[pos] = 4 * (q0 + u * qstep) + e;
+        }
+      }
+  }
+  sm = block_sum(sm, fscratch);
+  __syncthreads();
+  const int ncand = s_ncand;
+  if (ncand <= kCap) {
+    // ---- the few candidates: exact values, then the best `beam` by (value, lowest flat index)
+    if (threadIdx.x < kCap) {
+      Cand c;
+      c.v = -INFINITY;
+      c.idx = 0x7fffffff;
+      if (threadIdx.x < ncand) {
+        const int v = cidx[threadIdx.x];
+        const float x = row[v];
+        const float lp = logf(expf((unit_T ? x : x / T) - mx) / sm);  // softmax(-1).log()
+        c.v = first ? lp : (score + lp) / len;
+        c.idx = r * V + v;
+      }
+      cval[threadIdx.x] = c;
+    }
+    __syncthreads();
+    if (w == 0) {
+      Cand mine[kCap / 32];
+#pragma unroll
+      for (int j = 0; j < kCap / 32; ++j) mine[j] = cval[lane + 32 * j];
+      for (int k = 0; k < kMaxBeam; ++k) {
+        Cand best;
+        best.v = -INFINITY;
+        best.idx = 0x7fffffff;
+        int bj = -1;
+        if (k < beam) {
+#pragma unroll
+          for (int j = 0; j < kCap / 32; ++j)
+            if (mine[j].idx != 0x7fffffff && (bj < 0 || cand_better(mine[j], best))) { best = mine[j]; bj = j; }
+        }
+        Cand top = best;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          Cand oth;
+          oth.v = __shfl_xor_sync(0xffffffffu, top.v, o);
+          oth.idx = __shfl_xor_sync(0xffffffffu, top.idx, o);
+          if (oth.idx != 0x7fffffff && (top.idx == 0x7fffffff || cand_better(oth, top))) top = oth;
+        }
+        if (bj >= 0 && top.idx == best.idx) {
+#pragma unroll
+          for (int j = 0; j < kCap / 32; ++j)
+            if (j == bj) mine[j].idx = 0x7fffffff;
+        }
+        if (lane == 0) out[k] = top;
+      }
+    }
+    return;
+  }
 
+  // ---- more than kCap tokens at the threshold (rows full of equal logits): per-thread lists over the whole row
   // thread-local top-kMaxBeam candidates (fixed size keeps them in registers; top-beam is a subset)
   Cand loc[kMaxBeam];
 #pragma unroll
@@ -790,11 +938,13 @@ __global__ void __launch_bounds__(kSampThreads) beam_step_kernel(const BeamArgs 
     loc[q].v = -INFINITY;
     loc[q].idx = 0x7fffffff;
   }
-  auto push = [&](float val, int idx) {
+  for (int v = threadIdx.x; v < V; v += blockDim.x) {   // (ascending index per thread: a later token never wins a tie)
+    const float x = row[v];
+    const float lp = logf(expf((unit_T ? x : x / T) - mx) / sm);  // softmax(-1).log()
     Cand c;
-    c.v = val;
-    c.idx = idx;
-    if (!cand_better(c, loc[kMaxBeam - 1])) return;
+    c.v = first ? lp : (score + lp) / len;
+    c.idx = r * V + v;
+    if (!cand_better(c, loc[kMaxBeam - 1])) continue;
     loc[kMaxBeam - 1] = c;
 #pragma unroll
     for (int q = kMaxBeam - 1; q > 0; --q) {
@@ -804,23 +954,8 @@ __global__ void __launch_bounds__(kSampThreads) beam_step_kernel(const BeamArgs 
         loc[q - 1] = t;
       }
     }
-  };
-  for (int r = 0; r < rows; ++r) {
-    const float* row = a.logits + (first ? static_cast<long long>(n) : static_cast<long long>(n) * beam + r) * a.ld;
-    if (!first && s_stop[r]) {
-      // logits[has_stopped] = -inf; logits[has_stopped, 0] = 0  -> only token 0 is a finite candidate
-      if (threadIdx.x == 0) push((s_scores[r] + 0.f) / s_len[r], r * V);
-      continue;
-    }
-    const float mx = row_max[r], sm = row_lse_sum[r];
-    for (int v = threadIdx.x; v < V; v += blockDim.x) {
-      const float lp = logf(expf(row[v] / T - mx) / sm);  // softmax(-1).log()
-      const float val = first ? lp : (s_scores[r] + lp) / s_len[r];
-      push(val, r * V + v);
-    }
   }
   // warp merge: repeatedly extract the best head among the 32 lanes
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   {
     int head = 0;
     for (int k = 0; k < beam; ++k) {
@@ -830,10 +965,6 @@ __global__ void __launch_bounds__(kSampThreads) beam_step_kernel(const BeamArgs 
 #pragma unroll
       for (int q = 0; q < kMaxBeam; ++q)
         if (q == head) mine = loc[q];
-      if (head >= kMaxBeam) {
-        mine.v = -INFINITY;
-        mine.idx = 0x7fffffff;
-      }
       Cand best = mine;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
@@ -848,18 +979,58 @@ __global__ void __launch_bounds__(kSampThreads) beam_step_kernel(const BeamArgs 
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    // final merge of 32 sorted lists by one thread (32 * beam candidates)
-    int heads[32];
-    for (int q = 0; q < 32; ++q) heads[q] = 0;
-    const int nw = blockDim.x >> 5;
+    // final merge of the warps' sorted lists by one thread
+    int heads[kBeamRowThreads / 32];
+    for (int q = 0; q < nw; ++q) heads[q] = 0;
+    for (int k = 0; k < kMaxBeam; ++k) {
+      Cand best;
+      best.v = -INFINITY;
+      best.idx = 0x7fffffff;
+      if (k < beam) {
+        int bw = -1;
+        for (int q = 0; q < nw; ++q) {
+          if (heads[q] >= beam) continue;
+          const Cand c = wcand[q * kMaxBeam + heads[q]];
+          if (bw < 0 || cand_better(c, best)) {
+            best = c;
+            bw = q;
+          }
+        }
+        heads[bw]++;
+      }
+      out[k] = best;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) beam_merge_kernel(const BeamArgs a) {
+  __shared__ Cand top[kMaxBeam];
+  __shared__ float s_len[kMaxBeam];
+  __shared__ uint8_t s_stop[kMaxBeam];
+  extern __shared__ int perm_buf[];  // beam * max(max_len, max_pages) ints
+  const int n = blockIdx.x;
+  const int beam = a.beam, V = a.V;
+  const int step = *a.step;
+  const bool first = (step == 0);
+  const int rows = first ? 1 : beam;
+  if (threadIdx.x < beam) {
+    const uint8_t st = first ? 0 : a.has_stopped[n * beam + threadIdx.x];
+    s_stop[threadIdx.x] = st;
+    s_len[threadIdx.x] = first ? 1.f : a.seq_lengths[n * beam + threadIdx.x] + (st ? 0.f : 1.f);
+  }
+  if (threadIdx.x == 0) {
+    // merge of the rows' sorted candidate lists
+    const Cand* cand = a.cand + static_cast<long long>(n) * beam * kMaxBeam;
+    int heads[kMaxBeam];
+    for (int q = 0; q < kMaxBeam; ++q) heads[q] = 0;
     for (int k = 0; k < beam; ++k) {
       int bw = -1;
       Cand best;
       best.v = -INFINITY;
       best.idx = 0x7fffffff;
-      for (int q = 0; q < nw; ++q) {
+      for (int q = 0; q < rows; ++q) {
         if (heads[q] >= beam) continue;
-        const Cand c = wcand[q * kMaxBeam + heads[q]];
+        const Cand c = cand[q * kMaxBeam + heads[q]];
         if (bw < 0 || cand_better(c, best)) {
           best = c;
           bw = q;
@@ -1012,17 +1183,20 @@ int beam_step(const float* logits, long long ld, int N, int beam, int V, float t
   a.scores = st.scores; a.seq_lengths = st.seq_lengths; a.has_stopped = st.has_stopped; a.tokens = st.tokens;
   a.max_len = st.max_len; a.step = st.step; a.next_tokens = next_tokens; a.src_rows = src_rows;
   a.block_table = block_table; a.max_pages = max_pages; a.ctx_len = ctx_len;
+  if (st.cand_scratch == nullptr || st.cand_rows < N * beam) return (int)cudaErrorInvalidValue;
+  a.cand = static_cast<Cand*>(st.cand_scratch);
   const int m = st.max_len > max_pages ? st.max_len : max_pages;
   const size_t smem = static_cast<size_t>(beam) * m * sizeof(int);
   if (smem > 64 * 1024) return (int)cudaErrorInvalidValue;
   static bool configured_dev[kMaxDevices] = {};
   bool& configured = configured_dev[current_device_slot()];
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(beam_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(beam_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  beam_step_kernel<<<N, kSampThreads, smem, s>>>(a);
+  beam_rows_kernel<<<N * beam, kBeamRowThreads, 0, s>>>(a);
+  beam_merge_kernel<<<N, 256, smem, s>>>(a);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
 }
