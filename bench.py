@@ -18,6 +18,9 @@ replicated weights (weak scaling); the only collective is the final all-gather o
   cpu_baseline / --impl reference: the reference's own algorithm (batch-1 loop, full re-forward every token, fp32;
             inference.py:70-148 with beam_size=1) restated by oracle/clipcap_oracle.py, on the host cores.
 
+The default line (N = 1, config 2) also carries `other_configs`: short child runs (3 timed steps each) of BASELINE.json's
+configs 3 / 4 / 5 on the same GPU -- context, never part of `value` (--no-other-configs skips them).
+
 --config selects another BASELINE.json configuration (the default, 2, is the one the metric is quoted on and the only one
 the CPU arm covers): 3 = nucleus sampling (top_p 0.9, temperature 1.0), batch 256; 4 = beam 5, 102 images per step (two
 micro-batches of 51 = 255 rows, Engine.caption_dataset); 5 = GPT-J-6B + 4096-wide mapper, top_p 0.9, 16 images per GPU (128 on 8).
@@ -217,6 +220,27 @@ def cpu_baseline_leg():
                       "scaled x%.2f by sum(40+t) to a full caption" % (tok, NEW_TOKENS, scale)}
 
 
+def other_configs_leg():
+    """BASELINE.json's configs 3 / 4 / 5 on this GPU, each a short child run of this script (3 timed steps), so that the
+    driver's default invocation also carries their numbers.  Context for the headline line, never part of its `value`; a
+    child that fails or overruns its time limit is reported as such and does not affect the line."""
+    out = {}
+    for cfg_id, limit in ((3, 150), (4, 150), (5, 240)):
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--config", str(cfg_id), "--steps", "3", "--warmup", "3",
+                                "--no-cpu-baseline"], capture_output=True, text=True, timeout=limit,
+                               env={k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
+            j = json.loads(r.stdout.strip().splitlines()[-1])
+            out["config%d" % cfg_id] = {
+                "metric": j["metric"], "workload": j["config"]["workload"], "value": j["value"], "unit": j["unit"],
+                "e2e": j["e2e"]["value"], "ms_per_step": j["ms_per_step"], "steps": j["steps"],
+                "decode_step_ms": j["roofline"]["ms_per_launch"], "decode_step_gbs": j["roofline"]["achieved"],
+                "roofline_frac": j["roofline"]["frac"], "gpu_launches": j["gpu_launches"]}
+        except Exception as e:   # noqa: BLE001 -- context only
+            out["config%d" % cfg_id] = {"unavailable": "%s: %s" % (type(e).__name__, str(e)[:200])}
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -226,6 +250,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
+    ap.add_argument("--no-other-configs", action="store_true",
+                    help="skip the short runs of BASELINE.json's configs 3 / 4 / 5 that the default N=1 line reports under `other_configs`")
     args = ap.parse_args()
     C_ = CONFIGS[args.config]
     BATCH = C_["batch"]
@@ -339,6 +365,12 @@ def main():
         cpu = None
         if world == 1 and not args.no_cpu_baseline and args.config == 2:
             cpu = cpu_baseline_leg()
+        other = None
+        if world == 1 and args.config == 2 and not args.no_other_configs and not profiled:
+            # free this process's engine first: the GPT-J-6B run needs its own 12 GB of weights
+            eng.close()
+            torch.cuda.empty_cache()
+            other = other_configs_leg()
         line = {
             "metric": C_["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -360,6 +392,8 @@ def main():
                          "bytes_per_launch": step_bytes, "ms_per_launch": step_ms, "peak_source": peak_src},
             "cpu_baseline": cpu,
         }
+        if other is not None:
+            line["other_configs"] = other
         print(json.dumps(line), file=_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
