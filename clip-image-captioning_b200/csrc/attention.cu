@@ -174,15 +174,30 @@ __global__ void __launch_bounds__(256) attention_prefill_mma_kernel(
   ptx::grid_dep_wait();     // qkv comes from the c_attn GEMM this kernel is chained behind (PDL)
   ptx::grid_dep_launch();
 
-  // ---- stage K / V (16-byte chunks, zero padded), append them to the KV cache, build the key mask
+  // ---- stage K / V (16-byte chunks, zero padded), append them to the KV cache, build the key mask.
+  // Every chunk is requested with cp.async before the first one is used: a loop of load -> store per chunk has one
+  // L2 round trip per iteration on its critical path (the mapper's 80 x 27 chunks on 160 threads: 14 of them).
   const int cpr = HDP / 8;                // chunks per staged row
-  for (int idx = threadIdx.x; idx < S16 * cpr; idx += blockDim.x) {
-    const int j = idx / cpr, c = idx - j * cpr;
-    uint4 kk = make_uint4(0u, 0u, 0u, 0u), vv = kk;
-    if (j < S && c * 8 < hd) {
-      const bf16* rowp = base + static_cast<size_t>(j) * 3 * d + h * hd + c * 8;
-      kk = *reinterpret_cast<const uint4*>(rowp + d);
-      vv = *reinterpret_cast<const uint4*>(rowp + 2 * d);
+  {
+    const uint32_t ks_u32 = ptx::smem_u32(Ks), vs_u32 = ptx::smem_u32(Vs);
+    for (int idx = threadIdx.x; idx < S16 * cpr; idx += blockDim.x) {
+      const int j = idx / cpr, c = idx - j * cpr;
+      const bool ok = j < S && c * 8 < hd;
+      const bf16* rowp = ok ? base + static_cast<size_t>(j) * 3 * d + h * hd + c * 8 : base;
+      const uint32_t off = static_cast<uint32_t>((j * HDP + c * 8) * 2);
+      const uint32_t nbytes = ok ? 16u : 0u;   // 0: the chunk is zero-filled
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(ks_u32 + off), "l"(rowp + (ok ? d : 0)), "r"(nbytes) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(vs_u32 + off), "l"(rowp + (ok ? 2 * d : 0)), "r"(nbytes) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  }
+  if (rotary_dim > 0 || write_cache) {
+    // (each thread revisits the chunks it requested itself: its own cp.async writes are visible to it after the wait)
+    for (int idx = threadIdx.x; idx < S16 * cpr; idx += blockDim.x) {
+      const int j = idx / cpr, c = idx - j * cpr;
+      if (!(j < S && c * 8 < hd)) continue;
+      uint4 kk = *reinterpret_cast<const uint4*>(Ks + j * HDP + c * 8);
       if (c * 8 < rotary_dim) {   // GPT-J rotary on the first rotary_dim dims of K (pairs 2i, 2i+1), rounded to bf16 as cached
         uint32_t* kw = reinterpret_cast<uint32_t*>(&kk);
 #pragma unroll
@@ -193,8 +208,10 @@ __global__ void __launch_bounds__(256) attention_prefill_mma_kernel(
             kw[e] = pack_bf16x2(kf.x, kf.y);
           }
         }
+        *reinterpret_cast<uint4*>(Ks + j * HDP + c * 8) = kk;
       }
       if (write_cache) {
+        const uint4 vv = *reinterpret_cast<const uint4*>(Vs + j * HDP + c * 8);
         const int pos = pos0 + j;
         const int page = block_table[static_cast<size_t>(b) * cache.max_pages_per_row + pos / cache.page_tokens];
         const int tin = pos % cache.page_tokens;
@@ -202,8 +219,6 @@ __global__ void __launch_bounds__(256) attention_prefill_mma_kernel(
         *reinterpret_cast<uint4*>(cache.base + kv_index(cache, layer, 1, page, h, tin) + c * 8) = vv;
       }
     }
-    *reinterpret_cast<uint4*>(Ks + j * HDP + c * 8) = kk;
-    *reinterpret_cast<uint4*>(Vs + j * HDP + c * 8) = vv;
   }
   for (int j = threadIdx.x; j < S16; j += blockDim.x)
     mask_add[j] = (j < S && (key_mask == nullptr || key_mask[static_cast<size_t>(b) * S + j])) ? 0.f : -INFINITY;
@@ -404,23 +419,35 @@ __global__ void __launch_bounds__(128) attention_prefill_umma_kernel(
   ptx::grid_dep_wait();     // qkv comes from the c_attn GEMM this kernel is chained behind (PDL)
   ptx::grid_dep_launch();
   // ---- stage Q and K (row-major, swizzled), append K to the cache, key mask; then S = Q K^T is issued ...
+  // All twelve 16-byte chunks of a thread (Q, K, V of its four (key, chunk) pairs) are requested before the first one is
+  // stored: the shared-memory stores are asm volatile, so a load -> store loop would put one L2 round trip per iteration
+  // (eight in all) on the critical path of a CTA that lives for a few microseconds.
   const bf16* base = qkv + static_cast<size_t>(b) * S * 3 * d + h * HD;
   const int* bt = block_table + static_cast<size_t>(b) * cache.max_pages_per_row;
-  for (int idx = tid; idx < 64 * 8; idx += 128) {
+  uint4 q4[4], k4[4], v4[4];
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int idx = tid + it * 128;
     const int j = idx >> 3, c = idx & 7;
-    uint4 qq = make_uint4(0u, 0u, 0u, 0u), kk = qq;
+    q4[it] = k4[it] = v4[it] = make_uint4(0u, 0u, 0u, 0u);
     if (j < S) {
       const bf16* rowp = base + static_cast<size_t>(j) * 3 * d + c * 8;
-      qq = *reinterpret_cast<const uint4*>(rowp);
-      kk = *reinterpret_cast<const uint4*>(rowp + d);
-      if (write_cache) {
-        const int pos = pos0 + j;
-        *reinterpret_cast<uint4*>(cache.base + kv_index(cache, layer, 0, bt[pos / cache.page_tokens], h, pos % cache.page_tokens) + c * 8) = kk;
-      }
+      q4[it] = *reinterpret_cast<const uint4*>(rowp);
+      k4[it] = *reinterpret_cast<const uint4*>(rowp + d);
+      v4[it] = *reinterpret_cast<const uint4*>(rowp + 2 * d);
+    }
+  }
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int idx = tid + it * 128;
+    const int j = idx >> 3, c = idx & 7;
+    if (j < S && write_cache) {
+      const int pos = pos0 + j;
+      *reinterpret_cast<uint4*>(cache.base + kv_index(cache, layer, 0, bt[pos / cache.page_tokens], h, pos % cache.page_tokens) + c * 8) = k4[it];
     }
     const uint32_t off = static_cast<uint32_t>(j) * 128u + (static_cast<uint32_t>(c ^ (j & 7)) << 4);
-    sts_v4(q_s + off, qq);
-    sts_v4(k_s + off, kk);
+    sts_v4(q_s + off, q4[it]);
+    sts_v4(k_s + off, k4[it]);
   }
   if (tid < 64) mask_add[tid] = (tid < S && (key_mask == nullptr || key_mask[static_cast<size_t>(b) * S + tid])) ? 0.f : -INFINITY;
   ptx::fence_proxy_async();          // generic stores -> tcgen05.mma (async proxy) reads
@@ -438,15 +465,14 @@ __global__ void __launch_bounds__(128) attention_prefill_umma_kernel(
   // ---- ... while V is transposed: element (dim n, key j) -> row n, 16-byte chunk (j / 8) ^ (n % 8), slot j % 8.  A lane's
   // eight elements are visited in an order rotated by its chunk index c, so that the eight lanes that share a key write
   // eight different rows AND chunks (no bank conflicts; the loads stay 128 contiguous bytes per key)
-  for (int idx = tid; idx < 64 * 8; idx += 128) {
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int idx = tid + it * 128;
     const int j = idx >> 3, c = idx & 7;
-    uint4 vv = make_uint4(0u, 0u, 0u, 0u);
-    if (j < S) {
-      vv = *reinterpret_cast<const uint4*>(base + static_cast<size_t>(j) * 3 * d + 2 * d + c * 8);
-      if (write_cache) {
-        const int pos = pos0 + j;
-        *reinterpret_cast<uint4*>(cache.base + kv_index(cache, layer, 1, bt[pos / cache.page_tokens], h, pos % cache.page_tokens) + c * 8) = vv;
-      }
+    const uint4 vv = v4[it];
+    if (j < S && write_cache) {
+      const int pos = pos0 + j;
+      *reinterpret_cast<uint4*>(cache.base + kv_index(cache, layer, 1, bt[pos / cache.page_tokens], h, pos % cache.page_tokens) + c * 8) = vv;
     }
     const uint64_t lo64 = static_cast<uint64_t>(vv.x) | (static_cast<uint64_t>(vv.y) << 32);
     const uint64_t hi64 = static_cast<uint64_t>(vv.z) | (static_cast<uint64_t>(vv.w) << 32);
