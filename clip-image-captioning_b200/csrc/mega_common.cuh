@@ -271,6 +271,10 @@ __device__ __noinline__ void attention_phase(const Params& p, ComputeCtx& cc, in
       const float* src0 = ws + static_cast<uint32_t>(b) * rows_out + h * HD + dim;
       float2 w[3][8];
       int nsl[3];
+      // (the bias of this head's q / k / v slices is requested together with the partials: one round trip, not two)
+      float2 bqkv[3];
+#pragma unroll
+      for (int pz = 0; pz < 3; ++pz) bqkv[pz] = __ldg(reinterpret_cast<const float2*>(bias + pz * d + h * HD + dim));
 #pragma unroll
       for (int pz = 0; pz < 3; ++pz) {
         nsl[pz] = static_cast<int>(tbl[tbl_off + ((pz * d + h * HD) >> 7)] >> 16);
@@ -290,7 +294,7 @@ __device__ __noinline__ void attention_phase(const Params& p, ComputeCtx& cc, in
           const float2 e = ldcg_f2(src0 + pz * d + sl * slot_stride);
           acc.x += e.x; acc.y += e.y;
         }
-        const float2 bb = __ldg(reinterpret_cast<const float2*>(bias + pz * d + h * HD + dim));
+        const float2 bb = bqkv[pz];
         // the operator-per-kernel path stores c_attn's output as bf16: keep the same rounding
         part[pz] = unpack_bf16x2(pack_bf16x2(acc.x + bb.x, acc.y + bb.y));
       }
