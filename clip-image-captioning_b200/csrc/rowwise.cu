@@ -28,6 +28,56 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   ptx::grid_dep_wait();
   ptx::grid_dep_launch();
   const float* xr = x + static_cast<long long>(blockIdx.x) * ldx;
+  if (d <= 4 * 4 * static_cast<int>(blockDim.x) && blockDim.x == 256) {
+    // up to four 16-byte chunks per thread (d <= 4096): the row, gamma and beta are all requested before anything is
+    // used -- ONE L2 round trip where the loops below have one per iteration (eight at d = 4096: this kernel is on the
+    // critical path of every layer of the operator-chain decode step).  Same summation order as the loops.
+    float4 v[4], g[4], bb[4];
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = (threadIdx.x + i * 256) * 4;
+      const bool ok = c < d;
+      v[i] = ok ? *reinterpret_cast<const float4*>(xr + c) : z4;
+      g[i] = ok ? __ldg(reinterpret_cast<const float4*>(gamma + c)) : z4;
+      bb[i] = ok ? __ldg(reinterpret_cast<const float4*>(beta + c)) : z4;
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if ((threadIdx.x + i * 256) * 4 < d) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    const float mean = block_sum(s, scratch) / d;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if ((threadIdx.x + i * 256) * 4 < d) {
+        const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, dd = v[i].w - mean;
+        q += (a * a + b * b) + (cc * cc + dd * dd);
+      }
+    }
+    const float var = block_sum(q, scratch) / d;
+    const float rstd = rsqrtf(var + eps);
+    OutT* yr = y + static_cast<long long>(blockIdx.x) * ldy;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = (threadIdx.x + i * 256) * 4;
+      if (c < d) {
+        const float o0 = (v[i].x - mean) * rstd * g[i].x + bb[i].x;
+        const float o1 = (v[i].y - mean) * rstd * g[i].y + bb[i].y;
+        const float o2 = (v[i].z - mean) * rstd * g[i].z + bb[i].z;
+        const float o3 = (v[i].w - mean) * rstd * g[i].w + bb[i].w;
+        if constexpr (sizeof(OutT) == 2) {
+          uint2 pk;
+          pk.x = pack_bf16x2(o0, o1);
+          pk.y = pack_bf16x2(o2, o3);
+          *reinterpret_cast<uint2*>(yr + c) = pk;
+        } else {
+          *reinterpret_cast<float4*>(yr + c) = make_float4(o0, o1, o2, o3);
+        }
+      }
+    }
+    return;
+  }
   float s = 0.f;
   for (int c = threadIdx.x * 4; c < d; c += blockDim.x * 4) {
     const float4 v = *reinterpret_cast<const float4*>(xr + c);
