@@ -179,7 +179,8 @@ CCB_API int ccb_cross_entropy(ccb_ctx* ctx, const float* logits, int64_t ld, int
                const int32_t* row_map, int ignore_index, float* row_loss, float* loss_out, void* stream);
 /* one beam-search step on caller state (inference.py:98-131): logits [N*beam, ld] (step 0: [N, ld]);
  * scores/seq_lengths [N,beam] f32, has_stopped [N,beam] uint8, tokens [N,beam,max_len] int32 updated in place;
- * next_tokens / src_rows [N*beam] int32 out. */
+ * next_tokens / src_rows [N*beam] int32 out.  N * beam must not exceed the context's rows (max_images * max_beam): the
+ * rows' candidate lists are staged in a buffer of the context (two launches: rows, then the per-image merge). */
 CCB_API int ccb_beam_step(ccb_ctx* ctx, const float* logits, int64_t ld, int N, int beam, int V, float temperature,
                   int stop_token, int step, float* scores, float* seq_lengths, uint8_t* has_stopped,
                   int32_t* tokens, int max_len, int32_t* next_tokens, int32_t* src_rows, void* stream);
