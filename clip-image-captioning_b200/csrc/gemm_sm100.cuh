@@ -47,7 +47,7 @@ template <int BN>
 struct GemmCfg {
   static constexpr int BM = 128;
   static constexpr int BK = 64;
-  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 5 : (BN >= 64 ? 4 : 3));   // BN = 32: two CTAs per SM
+  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 5 : 3);   // BN = 32: two CTAs per SM; BN = 64 without split-K: three
   static constexpr int kMinBlocks = 1;
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
