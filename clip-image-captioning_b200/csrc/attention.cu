@@ -228,19 +228,27 @@ __global__ void __launch_bounds__(256) attention_prefill_mma_kernel(
   if (r0 >= S) return;
   const int row_a = r0 + g, row_b = r0 + g + 8;
 
-  // ---- Q fragments straight from global memory (A operand, row-major)
-  uint32_t qf[KS][4];
-  {
-    const bf16* qa = base + static_cast<size_t>(row_a) * 3 * d + h * hd;
-    const bf16* qb = base + static_cast<size_t>(row_b) * 3 * d + h * hd;
+  // ---- Q fragments straight from global memory (A operand, row-major), scores = Q K^T
+  constexpr bool kStreamQ = KS > 16;   // head_dim 512 (the 4096-wide mapper): KS x 4 fragment registers do not fit
+  const bf16* qa = base + static_cast<size_t>(row_a) * 3 * d + h * hd;
+  const bf16* qb = base + static_cast<size_t>(row_b) * 3 * d + h * hd;
+  auto load_q = [&](int ks, uint32_t (&f)[4]) {
+    const int k0 = ks * 16 + 2 * t, k1 = k0 + 8;
+    f[0] = (row_a < S && k0 < hd) ? *reinterpret_cast<const uint32_t*>(qa + k0) : 0u;
+    f[1] = (row_b < S && k0 < hd) ? *reinterpret_cast<const uint32_t*>(qb + k0) : 0u;
+    f[2] = (row_a < S && k1 < hd) ? *reinterpret_cast<const uint32_t*>(qa + k1) : 0u;
+    f[3] = (row_b < S && k1 < hd) ? *reinterpret_cast<const uint32_t*>(qb + k1) : 0u;
+  };
+  float sc[NT][4];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+  if constexpr (!kStreamQ) {
+    uint32_t qf[KS][4];
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
-      const int k0 = ks * 16 + 2 * t, k1 = k0 + 8;
-      qf[ks][0] = (row_a < S && k0 < hd) ? *reinterpret_cast<const uint32_t*>(qa + k0) : 0u;
-      qf[ks][1] = (row_b < S && k0 < hd) ? *reinterpret_cast<const uint32_t*>(qb + k0) : 0u;
-      qf[ks][2] = (row_a < S && k1 < hd) ? *reinterpret_cast<const uint32_t*>(qa + k1) : 0u;
-      qf[ks][3] = (row_b < S && k1 < hd) ? *reinterpret_cast<const uint32_t*>(qb + k1) : 0u;
+      load_q(ks, qf[ks]);
       if (ks * 16 < rotary_dim) {   // rotary on q (the MMA operand is bf16: the rotated pair is rounded once more)
+        const int k0 = ks * 16 + 2 * t, k1 = k0 + 8;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int k = (e < 2) ? k0 : k1;
@@ -253,18 +261,33 @@ __global__ void __launch_bounds__(256) attention_prefill_mma_kernel(
         }
       }
     }
-  }
-  // ---- scores = Q K^T
-  float sc[NT][4];
 #pragma unroll
-  for (int nt = 0; nt < NT; ++nt) {
-    sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
-    const bf16* krow = Ks + (nt * 8 + g) * HDP + 2 * t;
+    for (int nt = 0; nt < NT; ++nt) {
+      const bf16* krow = Ks + (nt * 8 + g) * HDP + 2 * t;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(krow + ks * 16);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(krow + ks * 16 + 8);
+        mma_bf16_16816(sc[nt], qf[ks], b0, b1);
+      }
+    }
+  } else {
+    // the scores accumulate head_dim step by step; the fragments of a step are requested four steps ahead (no rotary
+    // on this path: the host sends rotary models to the variants above)
+    uint32_t qr[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) load_q(i, qr[i]);
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
-      const uint32_t b0 = *reinterpret_cast<const uint32_t*>(krow + ks * 16);
-      const uint32_t b1 = *reinterpret_cast<const uint32_t*>(krow + ks * 16 + 8);
-      mma_bf16_16816(sc[nt], qf[ks], b0, b1);
+      uint32_t cur[4] = {qr[ks & 3][0], qr[ks & 3][1], qr[ks & 3][2], qr[ks & 3][3]};
+      if (ks + 4 < KS) load_q(ks + 4, qr[ks & 3]);
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const bf16* krow = Ks + (nt * 8 + g) * HDP + 2 * t;
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(krow + ks * 16);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(krow + ks * 16 + 8);
+        mma_bf16_16816(sc[nt], cur, b0, b1);
+      }
     }
   }
   // ---- mask, softmax over the row (thread holds keys nt*8 + 2t, +1 of rows a and b; the 4 lanes of a quad share a row)
@@ -917,6 +940,13 @@ int attention_prefill(const bf16* qkv, bf16* out, int B, int S, int H, int hd, f
     KvCache c;
     if (cache) c = *cache;
     return launch_prefill_umma(qkv, out, B, S, H, scale, causal, c, layer, block_table, pos0, cache != nullptr ? 1 : 0, key_mask, s);
+  }
+  if (use_mma && S <= 80 && hd % 8 == 0 && hd > 256 && hd <= 512 && rotary_dim == 0) {
+    // head_dim 512 (the 4096-wide mapper of config 5): K / V of 80 keys fill 166 KB, Q fragments are streamed
+    KvCache c;
+    if (cache) c = *cache;
+    return launch_prefill_mma<10, 32>(qkv, out, B, S, H, hd, scale, causal, c, layer, block_table, pos0, cache != nullptr ? 1 : 0, key_mask,
+                                      rotary_dim, s);
   }
   if (use_mma && S <= 128 && hd % 8 == 0 && hd <= 256 && rotary_dim % 2 == 0) {
     KvCache c;

@@ -109,6 +109,8 @@ def _ref_attention(qkv, B, S, H, hd, causal):
 
 @pytest.mark.parametrize("B,S,H,hd,causal", [(2, 50, 12, 64, False), (3, 80, 8, 200, False), (2, 20, 8, 96, False),
                                              (4, 40, 25, 64, True), (1, 80, 8, 512, False), (2, 41, 4, 256, True),
+                                             # head_dim above 256 (the 4096-wide mapper): Q fragments streamed, ragged S / head_dim, causal
+                                             (2, 33, 4, 512, True), (1, 80, 2, 320, False), (3, 7, 2, 512, False),
                                              # head_dim 64, S <= 64: the tcgen05 / TMEM kernel (full tile, one row, ragged)
                                              (1, 64, 3, 64, True), (3, 1, 2, 64, True), (2, 17, 5, 64, False), (2, 64, 2, 64, False)])
 def test_attention(tiny_engine, B, S, H, hd, causal):
