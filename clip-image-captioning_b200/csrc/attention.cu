@@ -783,7 +783,11 @@ __global__ void __launch_bounds__(kWideThreads) attention_decode_wide_kernel(
   float* qs = reinterpret_cast<float*>(Vs + static_cast<size_t>(tile) * HD * 2);   // [HD]
   float* sc = qs + HD;                                        // [tile]
   float* red = sc + tile;                                     // [2 * NW]
-  ptx::grid_dep_wait();
+  // Launched behind the q/k/v GEMM of the layer with programmatic stream serialization.  The context length, the block
+  // table and the CACHED K / V rows do not depend on that GEMM (they were written by earlier steps; everything up to the
+  // previous layer's last GEMM is complete once this kernel is resident, because the LayerNorm in between waits before it
+  // lets its successor start): they are requested before the dependency wait, so the HBM round trips of the first tile
+  // run underneath the GEMM's tail on every SM that has room for this CTA.  Only q / k_new / v_new wait.
   ptx::grid_dep_launch();
   const int unit = blockIdx.x;
   const int b = unit / H, h = unit - b * H;
@@ -808,6 +812,7 @@ __global__ void __launch_bounds__(kWideThreads) attention_decode_wide_kernel(
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   issue_tile(0);
+  ptx::grid_dep_wait();
 
   // ---- q / k_new / v_new: thread owns dims (2 tid, 2 tid + 1); rotary on q and k_new; append to the cache
   float vnx = 0.f, vny = 0.f, s_part = 0.f;
