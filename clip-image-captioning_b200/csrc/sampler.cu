@@ -8,6 +8,11 @@
 // shared-memory atomics), accumulating probability mass in double.  The kept set is identical to the
 // reference's "sort, cumsum, shift-right" rule: an element is kept iff the mass of the elements ranked
 // strictly before it is <= top_p (the first element crossing the threshold is kept, the top-1 always).
+// When only the sampled token is asked for (top-p, no typical-p, no filtered logits, no second draw) the boundary is
+// not needed at all: nucleus_sample_fast tests the best few candidates of argmax(p / q) for membership with that rule
+// and falls back to the select on a miss or a near-tie.
+// The beam step is two launches: beam_rows_kernel (one CTA per (image, beam row): the row's candidates) and
+// beam_merge_kernel (one CTA per image: merge, bookkeeping, block-table permutation).
 #include <float.h>
 
 #include "common.cuh"
