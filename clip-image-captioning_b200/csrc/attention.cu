@@ -155,7 +155,10 @@ __device__ __forceinline__ void ldmatrix_x2_trans(uint32_t& r0, uint32_t& r1, ui
   asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
 }
 
-template <int NT, int KS>   // NT: key tiles of 8 (even, >= 2 * warps); KS: head_dim steps of 16
+// OVL: K and V share ONE staging buffer (V is requested once every warp has its scores in registers): half the shared memory,
+// twice the CTAs per SM -- the mapper's 80 keys x head_dim 200 (69 KB for both) ran 512 CTAs on 444 slots, i.e. in two waves.
+// Only without rotary / cache append (the host picks it for the mapper shapes).
+template <int NT, int KS, bool OVL = false>   // NT: key tiles of 8 (even, >= 2 * warps); KS: head_dim steps of 16
 __global__ void __launch_bounds__(256) attention_prefill_mma_kernel(
     const bf16* __restrict__ qkv, bf16* __restrict__ out, int S, int H, int hd, float scale, int causal,
     KvCache cache, int layer, const int* __restrict__ block_table, int pos0, int write_cache,
@@ -166,7 +169,7 @@ __global__ void __launch_bounds__(256) attention_prefill_mma_kernel(
   const int HDP = KS * 16 + 8;            // row pitch in elements
   const int S16 = NT * 8;                 // staged key rows
   bf16* Ks = reinterpret_cast<bf16*>(smem_u4);
-  bf16* Vs = Ks + S16 * HDP;
+  bf16* Vs = OVL ? Ks : Ks + S16 * HDP;
   float* mask_add = reinterpret_cast<float*>(Vs + S16 * HDP);   // 0 or -inf per key
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -187,7 +190,8 @@ __global__ void __launch_bounds__(256) attention_prefill_mma_kernel(
       const uint32_t off = static_cast<uint32_t>((j * HDP + c * 8) * 2);
       const uint32_t nbytes = ok ? 16u : 0u;   // 0: the chunk is zero-filled
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(ks_u32 + off), "l"(rowp + (ok ? d : 0)), "r"(nbytes) : "memory");
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(vs_u32 + off), "l"(rowp + (ok ? 2 * d : 0)), "r"(nbytes) : "memory");
+      if constexpr (!OVL)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(vs_u32 + off), "l"(rowp + (ok ? 2 * d : 0)), "r"(nbytes) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -225,7 +229,7 @@ __global__ void __launch_bounds__(256) attention_prefill_mma_kernel(
   __syncthreads();
 
   const int r0 = warp * 16;               // this warp's query rows r0 + g, r0 + g + 8
-  if (r0 >= S) return;
+  if (!OVL && r0 >= S) return;            // (the launch has ceil(S / 16) warps: never taken; OVL has barriers below)
   const int row_a = r0 + g, row_b = r0 + g + 8;
 
   // ---- Q fragments straight from global memory (A operand, row-major), scores = Q K^T
@@ -346,6 +350,20 @@ __global__ void __launch_bounds__(256) attention_prefill_mma_kernel(
       pl[kk][q] = pack_bf16x2(x0 - hf.x, x1 - hf.y);
     }
   }
+  if constexpr (OVL) {
+    __syncthreads();   // every warp has read its K fragments: the buffer takes V now
+    const uint32_t vdst = ptx::smem_u32(Vs);
+    for (int idx = threadIdx.x; idx < S16 * cpr; idx += blockDim.x) {
+      const int j = idx / cpr, c = idx - j * cpr;
+      const bool ok = j < S && c * 8 < hd;
+      const bf16* rowp = ok ? base + static_cast<size_t>(j) * 3 * d + h * hd + c * 8 + 2 * d : base;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(vdst + static_cast<uint32_t>((j * HDP + c * 8) * 2)), "l"(rowp),
+                   "r"(ok ? 16u : 0u) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+  }
   // ---- O = P V, 64 output dims at a time
   const uint32_t vs_u32 = ptx::smem_u32(Vs);
   bf16* oa = out + (static_cast<size_t>(b) * S + row_a) * d + h * hd;
@@ -380,21 +398,21 @@ __global__ void __launch_bounds__(256) attention_prefill_mma_kernel(
   }
 }
 
-template <int NT, int KS>
+template <int NT, int KS, bool OVL = false>
 int launch_prefill_mma(const bf16* qkv, bf16* out, int B, int S, int H, int hd, float scale, int causal, const KvCache& c,
                        int layer, const int* block_table, int pos0, int write_cache, const uint8_t* key_mask, int rotary_dim,
                        cudaStream_t s) {
   const int HDP = KS * 16 + 8, S16 = NT * 8;
-  const size_t smem = static_cast<size_t>(2) * S16 * HDP * sizeof(bf16) + S16 * sizeof(float);
+  const size_t smem = static_cast<size_t>(OVL ? 1 : 2) * S16 * HDP * sizeof(bf16) + S16 * sizeof(float);
   static size_t configured_dev[kMaxDevices] = {};
   size_t& configured = configured_dev[current_device_slot()];
   if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_prefill_mma_kernel<NT, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    cudaError_t e = cudaFuncSetAttribute(attention_prefill_mma_kernel<NT, KS, OVL>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return (int)e;
     configured = smem;
   }
   const int warps = (S + 15) / 16;
-  cudaError_t e = launch_kernel(attention_prefill_mma_kernel<NT, KS>, dim3(H, B), dim3(warps * 32), smem, s, true, qkv, out, S, H, hd,
+  cudaError_t e = launch_kernel(attention_prefill_mma_kernel<NT, KS, OVL>, dim3(H, B), dim3(warps * 32), smem, s, true, qkv, out, S, H, hd,
                                 scale, causal, c, layer, block_table, pos0, write_cache, key_mask, rotary_dim);
   return e == cudaSuccess ? 0 : (int)e;
 }
@@ -950,14 +968,17 @@ int attention_prefill(const bf16* qkv, bf16* out, int B, int S, int H, int hd, f
     // head_dim 512 (the 4096-wide mapper of config 5): K / V of 80 keys fill 166 KB, Q fragments are streamed
     KvCache c;
     if (cache) c = *cache;
-    return launch_prefill_mma<10, 32>(qkv, out, B, S, H, hd, scale, causal, c, layer, block_table, pos0, cache != nullptr ? 1 : 0, key_mask,
-                                      rotary_dim, s);
+    if (cache == nullptr)
+      return launch_prefill_mma<10, 32, true>(qkv, out, B, S, H, hd, scale, causal, c, layer, block_table, pos0, 0, key_mask, rotary_dim, s);
+    return launch_prefill_mma<10, 32>(qkv, out, B, S, H, hd, scale, causal, c, layer, block_table, pos0, 1, key_mask, rotary_dim, s);
   }
   if (use_mma && S <= 128 && hd % 8 == 0 && hd <= 256 && rotary_dim % 2 == 0) {
     KvCache c;
     if (cache) c = *cache;
     const int wc = cache != nullptr ? 1 : 0;
     const int ks = (hd + 15) / 16, nt = 2 * ((S + 15) / 16);
+    if (nt > 8 && nt <= 10 && ks > 8 && ks <= 13 && cache == nullptr && rotary_dim == 0)   // the mapper: 80 keys x head_dim 200
+      return launch_prefill_mma<10, 13, true>(qkv, out, B, S, H, hd, scale, causal, c, layer, block_table, pos0, 0, key_mask, 0, s);
     if (nt <= 4) return dispatch_prefill_mma_ks<4>(ks, qkv, out, B, S, H, hd, scale, causal, c, layer, block_table, pos0, wc, key_mask, rotary_dim, s);
     if (nt <= 6) return dispatch_prefill_mma_ks<6>(ks, qkv, out, B, S, H, hd, scale, causal, c, layer, block_table, pos0, wc, key_mask, rotary_dim, s);
     if (nt <= 8) return dispatch_prefill_mma_ks<8>(ks, qkv, out, B, S, H, hd, scale, causal, c, layer, block_table, pos0, wc, key_mask, rotary_dim, s);
