@@ -652,7 +652,7 @@ constexpr int kDecodeWarps = 4;
 template <int HD>
 __global__ void __launch_bounds__(kDecodeWarps * 32) attention_decode_kernel(
     const bf16* __restrict__ qkv, bf16* __restrict__ out, int rows, int H, float scale, KvCache cache, int layer,
-    const int* __restrict__ block_table, const int* __restrict__ ctx_len, int rotary_dim, int sc_cap) {
+    const int* __restrict__ block_table, const int* __restrict__ ctx_len, int rotary_dim, int sc_cap, long long ldo) {
   constexpr int E = HD / 32;  // dims per lane in the "own dims" layout (2, 4, 8): pairs stay inside a lane
   extern __shared__ float dsm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -772,7 +772,7 @@ __global__ void __launch_bounds__(kDecodeWarps * 32) attention_decode_kernel(
     const int dim = c0 + 2 * lane;
     const float2 vn = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(row + 2 * d + h * HD + dim));
     const float o0 = (acc[0] + p_new * vn.x) * inv, o1 = (acc[1] + p_new * vn.y) * inv;
-    *reinterpret_cast<uint32_t*>(out + static_cast<size_t>(b) * d + h * HD + dim) = pack_bf16x2(o0, o1);
+    *reinterpret_cast<uint32_t*>(out + static_cast<size_t>(b) * ldo + h * HD + dim) = pack_bf16x2(o0, o1);
   }
 }
 
@@ -790,7 +790,7 @@ constexpr int kWideThreads = 128;
 template <int HD>
 __global__ void __launch_bounds__(kWideThreads) attention_decode_wide_kernel(
     const bf16* __restrict__ qkv, bf16* __restrict__ out, int rows, int H, float scale, KvCache cache, int layer,
-    const int* __restrict__ block_table, const int* __restrict__ ctx_len, int rotary_dim, int tile) {
+    const int* __restrict__ block_table, const int* __restrict__ ctx_len, int rotary_dim, int tile, long long ldo) {
   constexpr int CH = HD / 8;            // 16-byte chunks per K / V row
   constexpr int TPW = 32 / CH;          // tokens a warp scores per iteration (CH <= 32)
   constexpr int NW = kWideThreads / 32;
@@ -940,7 +940,7 @@ __global__ void __launch_bounds__(kWideThreads) attention_decode_wide_kernel(
   if (2 * tid < HD) {
     const float inv = 1.f / l_run;
     const float o0 = (accx + p_new * vnx) * inv, o1 = (accy + p_new * vny) * inv;
-    *reinterpret_cast<uint32_t*>(out + static_cast<size_t>(b) * d + h * HD + 2 * tid) = pack_bf16x2(o0, o1);
+    *reinterpret_cast<uint32_t*>(out + static_cast<size_t>(b) * ldo + h * HD + 2 * tid) = pack_bf16x2(o0, o1);
   }
 }
 
@@ -1005,9 +1005,10 @@ int attention_prefill(const bf16* qkv, bf16* out, int B, int S, int H, int hd, f
   return e == cudaSuccess ? 0 : (int)e;
 }
 
-int attention_decode(const bf16* qkv, bf16* out, int B, int H, int hd, float scale, const KvCache* cache, int layer,
+int attention_decode(const bf16* qkv, bf16* out, long long ldo, int B, int H, int hd, float scale, const KvCache* cache, int layer,
                      const int* block_table, const int* ctx_len, int rotary_dim, cudaStream_t s) {
   if (B <= 0) return 0;
+  if (ldo < static_cast<long long>(H) * hd || (ldo & 1)) return (int)cudaErrorInvalidValue;
   if (!cache) return (int)cudaErrorInvalidValue;
   // One CTA per (row, head) for head_dim 256 (GPT-J); CCB_ATTN_WIDE=1 / 0 forces it on / off for every head_dim.
   static const int wide_mode = [] {
@@ -1036,7 +1037,7 @@ int attention_decode(const bf16* qkv, bf16* out, int B, int H, int hd, float sca
       configured = 112 * 1024;                                                                                            \
     }                                                                                                                     \
     cudaError_t le = launch_kernel(attention_decode_wide_kernel<HDV>, dim3(B * H), dim3(kWideThreads), wsmem, s, true, qkv, \
-                                   out, B, H, scale, *cache, layer, block_table, ctx_len, rotary_dim, tile);              \
+                                   out, B, H, scale, *cache, layer, block_table, ctx_len, rotary_dim, tile, ldo);              \
     if (le != cudaSuccess) return (int)le;                                                                                \
   } while (0)
     if (hd == 64)
@@ -1067,7 +1068,7 @@ int attention_decode(const bf16* qkv, bf16* out, int B, int H, int hd, float sca
       configured = 200 * 1024;                                                                                      \
     }                                                                                                               \
     cudaError_t le = launch_kernel(attention_decode_kernel<HDV>, dim3(grid), dim3(kDecodeWarps * 32), smem, s, true, \
-                                   qkv, out, B, H, scale, *cache, layer, block_table, ctx_len, rotary_dim, sc_cap);   \
+                                   qkv, out, B, H, scale, *cache, layer, block_table, ctx_len, rotary_dim, sc_cap, ldo);   \
     if (le != cudaSuccess) return (int)le;                                                                          \
   } while (0)
   if (hd == 64)

@@ -187,7 +187,7 @@ std::string fmt(const char* f, ...) {
 
 // matrix [features, K] given as nn.Linear [out, in]
 void slot_linear(ccb_ctx* c, const std::string& base, Linear& L, bool bias_optional = false) {
-  add_slot(c, base + ".weight", WeightSlot::MATRIX, L.w, L.features, L.K, L.K);
+  add_slot(c, base + ".weight", WeightSlot::MATRIX, L.w, L.features, L.K, L.ldw ? L.ldw : L.K);
   if (L.has_bias || bias_optional)
     add_slot(c, base + ".bias", WeightSlot::VECTOR_F32, L.bias, L.features, 1, 1, &L.has_bias, bias_optional && !L.has_bias);
 }
@@ -211,6 +211,7 @@ int linear(ccb_ctx* c, const bf16* act, long long lda, int tokens, const Linear&
   g.lda = lda;
   g.tokens = tokens;
   g.weight = L.w;
+  g.ldw = L.ldw;
   g.features = L.features;
   g.K = L.K;
   g.bias = L.has_bias ? L.bias : nullptr;
@@ -542,12 +543,29 @@ int lm_decode_step(ccb_ctx* c, int rows, cudaStream_t s) {
   RUN(embed_tokens(c->wte, D.lm_arch == CCB_LM_GPT2 ? c->wpe : nullptr, c->next_tokens, c->ctx_len, c->h, rows, d, D.lm_vocab, D.lm_n_pos, s));
   const BlockShape sh = lm_shape(D);
   const float scale = 1.0f / sqrtf(static_cast<float>(hd));
+  static const bool fuse_out = [] {   // CCB_GPTJ_FUSE_OUT=0: out_proj and fc_out as two launches (A/B, tests)
+    const char* e = getenv("CCB_GPTJ_FUSE_OUT");
+    return !(e && e[0] == '0');
+  }();
   for (int l = 0; l < D.lm_layers; ++l) {
+    const Block& b = c->lm[l];
+    if (sh.parallel && fuse_out && b.projfc2.w != nullptr && c->attmlp != nullptr) {
+      // GPT-J: h += out_proj(att) + fc_out(gelu_new(fc_in(ln_1 h))) + b as ONE GEMM over K = 5 d.  The 32 x 8 CTAs of the
+      // stand-alone out_proj stream 33 MB at 2.6 TB/s (launch ramp, cluster reduce and epilogue around 8 k-blocks per CTA);
+      // as the first fifth of fc_out's K loop the same bytes move at that GEMM's 4.9 TB/s.
+      const long long ldc = 5LL * d;
+      RUN(layernorm_f32_bf16(c->h, d, b.ln1.g, b.ln1.b, sh.eps, c->x, d, rows, d, s));
+      RUN(linear(c, c->x, d, rows, b.qkv, CCB_ACT_NONE, nullptr, 0, c->qkv, 3 * d, 1, s));
+      RUN(attention_decode(c->qkv, c->attmlp, ldc, rows, H, hd, scale, &c->kv, l, c->block_table, c->ctx_len, D.lm_rotary_dim, s));
+      RUN(linear(c, c->x, d, rows, b.fc, sh.act, nullptr, 0, c->attmlp + d, ldc, 1, s));
+      RUN(linear(c, c->attmlp, ldc, rows, b.projfc2, CCB_ACT_NONE, c->h, d, c->h, d, 0, s));
+      continue;
+    }
     auto attn = [&]() {
-      return attention_decode(c->qkv, c->att, rows, H, hd, scale, &c->kv, l, c->block_table, c->ctx_len,
+      return attention_decode(c->qkv, c->att, d, rows, H, hd, scale, &c->kv, l, c->block_table, c->ctx_len,
                               D.lm_rotary_dim, s);
     };
-    if (block_forward(c, c->lm[l], rows, sh, attn, s)) return -1;
+    if (block_forward(c, b, rows, sh, attn, s)) return -1;
   }
   RUN(layernorm_f32_bf16(c->h, d, c->lm_lnf.g, c->lm_lnf.b, D.lm_ln_eps, c->x, d, rows, d, s));
   RUN(linear(c, c->x, d, rows, c->lm_head, CCB_ACT_NONE, nullptr, 0, c->logits, c->ldv, 0, s));
@@ -853,9 +871,27 @@ int ccb_create(ccb_ctx** out, const ccb_model_desc* desc, int device) {
       slot_conv1d(c, base + ".mlp.c_proj", b.fc2);
     } else {
       make_linear(c, a, b.qkv, 3 * d, d, false);
-      make_linear(c, a, b.proj, d, d, false);
       make_linear(c, a, b.fc, 4 * d, d, true);
-      make_linear(c, a, b.fc2, d, 4 * d, true);
+      {
+        // out_proj | fc_out side by side in one [d, 5d] matrix (engine.h: Block::projfc2); the prefill GEMMs read the two
+        // column ranges through their row pitch
+        bf16* cat = a.arr<bf16>(static_cast<size_t>(d) * 5 * d);
+        b.proj.w = cat;
+        b.proj.features = d;
+        b.proj.K = d;
+        b.proj.ldw = 5LL * d;
+        b.proj.bias = a.arr<float>(d);
+        b.proj.has_bias = false;
+        b.fc2.w = cat + d;
+        b.fc2.features = d;
+        b.fc2.K = 4 * d;
+        b.fc2.ldw = 5LL * d;
+        b.fc2.bias = a.arr<float>(d);
+        b.fc2.has_bias = true;
+        b.projfc2 = b.fc2;
+        b.projfc2.w = cat;
+        b.projfc2.K = 5 * d;
+      }
       add_slot(c, base + ".attn.q_proj.weight", WeightSlot::MATRIX, b.qkv.w, d, d, d);
       add_slot(c, base + ".attn.k_proj.weight", WeightSlot::MATRIX, b.qkv.w + static_cast<size_t>(d) * d, d, d, d);
       add_slot(c, base + ".attn.v_proj.weight", WeightSlot::MATRIX, b.qkv.w + 2 * static_cast<size_t>(d) * d, d, d, d);
@@ -1009,6 +1045,7 @@ int ccb_create(ccb_ctx** out, const ccb_model_desc* desc, int device) {
   c->qkv = a.arr<bf16>(Mz * 3 * c->dmax);
   c->att = a.arr<bf16>(Mz * c->dmax);
   c->mlp = a.arr<bf16>(Mz * c->hidden_max);
+  if (D.lm_arch == CCB_LM_GPTJ) c->attmlp = a.arr<bf16>(static_cast<size_t>(c->max_rows) * 5 * d);
   if (D.vit_present) {
     const int g = D.vit_image / D.vit_patch, np = g * g, kdim = 3 * D.vit_patch * D.vit_patch;
     c->patches = a.arr<bf16>(static_cast<size_t>(D.max_images) * np * kdim);

@@ -19,6 +19,7 @@ struct Linear {
   float* bias = nullptr;  // [features] or null
   int features = 0, K = 0;
   bool has_bias = false;
+  long long ldw = 0;      // row pitch in elements (0: K); wider for a view of a K-concatenated matrix
 };
 struct LayerNormW {
   float* g = nullptr;
@@ -27,6 +28,9 @@ struct LayerNormW {
 struct Block {            // one pre-LN transformer block (ViT / mapper / GPT-2 / GPT-J)
   LayerNormW ln1, ln2;
   Linear qkv, proj, fc, fc2;
+  // GPT-J (parallel block): out_proj and fc_out are the column ranges [0, d) and [d, 5d) of ONE [d, 5d] matrix, so that the
+  // decode step runs h += [att | gelu(fc_in)] . [W_out | W_fc_out]^T + b_fc_out as one weight-streaming GEMM (w == nullptr elsewhere)
+  Linear projfc2;
 };
 
 // a weight the loader expects: where it goes and how the caller tensor is repacked
@@ -98,6 +102,7 @@ struct ccb_ctx {
   ccb::bf16* qkv = nullptr;       // [M, 3*dmax]
   ccb::bf16* att = nullptr;       // [M, dmax]
   ccb::bf16* mlp = nullptr;       // [M, hidden_max]
+  ccb::bf16* attmlp = nullptr;    // GPT-J decode: [max_rows, 5 d] = [att | gelu(fc_in)], the fused GEMM's operand
   ccb::bf16* patches = nullptr;   // [B*np, 3*ps*ps]
   float* patch_emb = nullptr;     // [B*np, width]
   float* feat = nullptr;          // [B, vit_out] f32

@@ -151,7 +151,7 @@ int launch_persist(const GemmArgs& a, const GemmParams& p_in, int bn, bool pair,
   pp.n_tiles = (a.features + bn - 1) / bn;
   CUtensorMap tx, tw;
   if (make_tmap(&tx, a.act, a.tokens, a.K, a.lda, 128)) return -1;
-  if (make_tmap(&tw, a.weight, a.features, a.K, a.K, pair ? bn / 2 : bn)) return -1;
+  if (make_tmap(&tw, a.weight, a.features, a.K, a.ldw ? a.ldw : a.K, pair ? bn / 2 : bn)) return -1;
   const int tiles = pp.m_tiles * pp.n_tiles;
   const int units = pair ? num_sms / 2 : num_sms;
   cudaLaunchConfig_t cfg;
@@ -254,8 +254,9 @@ int gemm_launch(const GemmArgs& a, const GemmWorkspace& w, cudaStream_t stream) 
   const bf16* B = swapped ? a.act : a.weight;
   p.Ra = swapped ? a.features : a.tokens;
   p.Rb = swapped ? a.tokens : a.features;
-  const long long ldA = swapped ? a.K : a.lda;
-  const long long ldB = swapped ? a.lda : a.K;
+  const long long ldw = a.ldw ? a.ldw : a.K;
+  const long long ldA = swapped ? ldw : a.lda;
+  const long long ldB = swapped ? a.lda : ldw;
   p.k_blocks = a.K / 64;
   p.out = a.out;
   p.out_bf16 = a.out_bf16;

@@ -60,7 +60,8 @@ struct GemmArgs {
   const bf16* act = nullptr;   // [tokens, K] row-major, leading dim lda (elements)
   long long lda = 0;
   int tokens = 0;
-  const bf16* weight = nullptr;  // [features, K] row-major (K-major), leading dim K
+  const bf16* weight = nullptr;  // [features, K] row-major (K-major), leading dim ldw (0: K)
+  long long ldw = 0;
   int features = 0;
   int K = 0;                     // multiple of 64
   const float* bias = nullptr;   // [features] or null
@@ -140,8 +141,9 @@ int attention_prefill(const bf16* qkv, bf16* out, int B, int S, int H, int hd, f
                       const KvCache* cache, int layer, const int* block_table, int pos0, int rotary_dim,
                       const uint8_t* key_mask, cudaStream_t s);
 // One new token per row: appends this step's k/v (from qkv [B, 3*d]) at position ctx_len[b] and attends over
-// positions [0, ctx_len[b]] through the block table. ctx_len is device memory (graph-replay friendly).
-int attention_decode(const bf16* qkv, bf16* out, int B, int H, int hd, float scale, const KvCache* cache, int layer,
+// positions [0, ctx_len[b]] through the block table. ctx_len is device memory (graph-replay friendly).  `out` rows have pitch ldo
+// (elements): H * hd, or wider when the output lands in the [att | mlp] operand of GPT-J's fused out_proj + fc_out GEMM.
+int attention_decode(const bf16* qkv, bf16* out, long long ldo, int B, int H, int hd, float scale, const KvCache* cache, int layer,
                      const int* block_table, const int* ctx_len, int rotary_dim, cudaStream_t s);
 
 // ------------------------------------------------------------------ samplers (sampler.cu)
