@@ -3,18 +3,37 @@
 The reference needs packages that are not installed here (pytorch_lightning, clip, fire, skimage, pycocoevalcap,
 the Salesforce BLIP checkout).  None of them is on the caption-generation path itself, so they are replaced by
 empty import stubs; the reference's own files are imported as they lie (PYTHONDONTWRITEBYTECODE: the tree is
-read-only).  Used by tools/make_golden.py to produce tests/golden/*.pt and by bench.py --impl reference when the
-reference tree is present.  /root/reference does not exist on the GPU box: nothing that runs there may need this.
+read-only).  Used by tools/make_golden.py to produce tests/golden/*.pt and by bench.py's CPU arms (`--impl reference`, `cpu_baseline`).
+/root/reference does not exist on the GPU box: there the same modules are imported from oracle/_ref, the sourceless bytecode that
+`__graft_entry__.build()` compiles from the reference tree (oracle/build_ref.py); without either, `available()` is False and
+bench.py times the oracle's restatement instead.
 """
 import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("CLIPCAP_REFERENCE_ROOT", "/root/reference")
+COMPILED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")   # oracle/build_ref.py: sourceless .pyc
+
+
+def _pick_root() -> str:
+    env = os.environ.get("CLIPCAP_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/layers"):
+        return "/root/reference"
+    return COMPILED_ROOT
+
+
+REFERENCE_ROOT = _pick_root()
 
 
 def available() -> bool:
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "layers"))
+
+
+def kind() -> str:
+    """"source": the tree itself (build container); "compiled": oracle/_ref, the same modules byte-compiled by build()."""
+    return "compiled" if os.path.abspath(REFERENCE_ROOT) == COMPILED_ROOT else "source"
 
 
 def _stub(name, **attrs):
