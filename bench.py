@@ -234,11 +234,19 @@ def build_reference_arm(threads):
 
 
 def build_cpu_arm(threads):
+    """The reference's own loop where it imports and runs (one warm token first), else the oracle's restatement of it."""
     run = build_reference_arm(threads)
+    if run is not None:
+        try:
+            run(1)                            # warms the allocator / thread pool; a reference that cannot run here falls back
+        except Exception as e:   # noqa: BLE001
+            sys.stderr.write("bench.py: reference arm failed its warm run (%s: %s); timing the oracle port\n" % (type(e).__name__, str(e)[:300]))
+            run = None
     if run is None:
         run = build_oracle(threads)
         run.kind = "port"
         run.what = "reference no-KV-cache batch-1 loop restated by the oracle (oracle/clipcap_oracle.py), fp32"
+        run(1)
     return run
 
 
@@ -256,8 +264,7 @@ def run_reference(args):
     threads = os.cpu_count() or 1
     # bounded sample: one image, the first `tok` tokens of its caption; sized so W + K steps end in a few minutes
     budget_s = 150.0
-    run = build_cpu_arm(threads)
-    run(1)                                # warms the allocator / thread pool
+    run = build_cpu_arm(threads)          # (has run one warm token)
     per_full = run(2) * sample_scale(2)
     tok = NEW_TOKENS
     while tok > 2 and (args.steps + args.warmup) * per_full / sample_scale(tok) > budget_s:
@@ -283,7 +290,6 @@ def cpu_baseline_leg():
     """Reported baseline at N=1: ~10-30 s of the oracle on the host cores."""
     threads = os.cpu_count() or 1
     run = build_cpu_arm(threads)
-    run(1)
     t2 = run(2)
     tok = NEW_TOKENS
     while tok > 2 and t2 * sample_scale(2) / sample_scale(tok) > 25.0:
