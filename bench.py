@@ -16,7 +16,9 @@ replicated weights (weak scaling); the only collective is the final all-gather o
             HBM bytes (bf16 weights once + KV read/write) / its mean duration (events recorded by the
             library on its launching stream inside the timed region) against the measured HBM peak
   cpu_baseline / --impl reference: the reference's own algorithm (batch-1 loop, full re-forward every token, fp32;
-            inference.py:70-148 with beam_size=1) restated by oracle/clipcap_oracle.py, on the host cores.
+            inference.py:70-148 with beam_size=1) on the host cores -- the reference's own modules (kind "reference": imported
+            unmodified from /root/reference, or from oracle/_ref, the bytecode build() compiles from it, where that tree is
+            absent), else the restatement in oracle/clipcap_oracle.py (kind "port").
 
 The default line (N = 1, config 2) also carries `other_configs`: short child runs (3 timed steps each) of BASELINE.json's
 configs 3 / 4 / 5 on the same GPU -- context, never part of `value` (--no-other-configs skips them).
