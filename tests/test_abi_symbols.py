@@ -46,3 +46,21 @@ def test_no_cpu_fallback():
     with pytest.raises(Exception) as e:
         cc.Engine(cc.EngineConfig(lm_layers=1, map_layers=1, vit_layers=1, max_images=1))
     assert "CUDA" in str(e.value) or "device" in str(e.value)
+
+
+def test_product_path_never_touches_the_oracle():
+    """oracle/ is test / baseline infrastructure: only tests/, __graft_entry__.smoke() / build() and bench.py's CPU arms may
+    import, link or execute anything under it.  No file of the package (host Python, CUDA sources, headers) names it."""
+    import re
+    pkg = os.path.join(ROOT, "clip-image-captioning_b200")
+    offenders = []
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if not f.endswith((".py", ".cu", ".cuh", ".h")):
+                continue
+            text = open(os.path.join(dirpath, f), errors="ignore").read()
+            if re.search(r"clipcap_oracle|ref_harness|build_ref|[\"'/]oracle[\"'/]|import oracle|from oracle", text):
+                offenders.append(os.path.relpath(os.path.join(dirpath, f), ROOT))
+    assert not offenders, offenders
+    shim = open(os.path.join(ROOT, "clipcap_b200.py")).read()
+    assert "oracle" not in shim
